@@ -1,0 +1,539 @@
+/*
+ * capi.cu — the C ABI of libcpuvox_b200.so (include/cpuvox_b200.h): context, world upload, resolution, draw, readback.
+ * Replaces the body of RenderManager.DrawSegments (Assets/Code/RenderManager.cs:258-372), RayBuffer upload/copy
+ * (Assets/Code/Rendering/RayBuffer.cs:79-96) and BlitSegments (RenderManager.cs:199-256). No CPU fallback: every
+ * entry point that renders needs a CUDA device, and fails with an error code (never an exception) otherwise.
+ */
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/cpuvox_b200.h"
+#include "device_types.h"
+
+static_assert(sizeof(cvx_ray_state) == sizeof(cvxd_ray_state), "ray state layout");
+static_assert(sizeof(cvx_counters) == sizeof(cvxd_counters), "counter layout");
+static_assert(CVX_LOD_LEVELS == CVXD_LODS, "lod levels");
+
+struct cvx_ctx {
+    int device = 0;
+    int flags = 0;
+    cudaStream_t stream = nullptr;      // compute
+    cudaStream_t copyStream = nullptr;  // device->host frame copies of cvx_draw_batch
+    bool ownStream = true;
+    cvxd_world world;
+    void* lodHeaders[CVX_LOD_LEVELS];
+    void* lodElements[CVX_LOD_LEVELS];
+    int width = 0, height = 0;
+    uint32_t* td = nullptr;
+    uint32_t* lr = nullptr;
+    uint32_t* frames[2] = {nullptr, nullptr}; // internal framebuffers (double buffered for batches)
+    uint32_t* externalFrame = nullptr;
+    int frameIndex = 0;
+    cvxd_counters* counters = nullptr;
+    cudaEvent_t evStart = nullptr, evMid = nullptr, evEnd = nullptr;
+    cudaEvent_t evFrameDone[2] = {nullptr, nullptr}, evCopyDone[2] = {nullptr, nullptr};
+    bool timed = false;
+    int64_t launches = 0;
+    std::string error;
+};
+
+namespace {
+
+std::string g_createError;
+
+int fail(cvx_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->error = buf; else g_createError = buf;
+    return code;
+}
+
+#define CU(ctx, call)                                                                                     \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? CVX_ERR_OUT_OF_MEMORY : CVX_ERR_CUDA,      \
+                        "%s failed: %s", #call, cudaGetErrorString(e_));                                  \
+    } while (0)
+
+inline int f2i(float f) { return (f >= -2147483648.0f && f < 2147483648.0f) ? (int)f : (int)0x80000000; }
+inline int clampi(int x, int a, int b) { return x < a ? a : (x > b ? b : x); }
+
+// RenderManager.DrawSegments context fill, RenderManager.cs:281-318
+int fill_segments(const cvx_frame_setup* s, int W, int H, cvxd_segment out[4]) {
+    int total = 0;
+    const float vx = s->vanishing_point_screen[0], vy = s->vanishing_point_screen[1];
+    for (int k = 0; k < 4; k++) {
+        cvxd_segment& c = out[k];
+        memset(&c, 0, sizeof c);
+        const cvx_segment& in = s->segments[k];
+        c.ray_count = in.ray_count;
+        total += in.ray_count > 0 ? in.ray_count : 0;
+        for (int i = 0; i < 2; i++) {
+            c.ray_min[i] = in.cam_local_plane_ray_min[i]; c.ray_max[i] = in.cam_local_plane_ray_max[i];
+            c.min_screen[i] = in.min_screen[i]; c.max_screen[i] = in.max_screen[i];
+        }
+        if (in.ray_count <= 0) continue;
+        c.axis_mapped_to_y = k > 1 ? 0 : 1;
+        c.ray_index_offset = k == 1 ? s->segments[0].ray_count : (k == 3 ? s->segments[2].ray_count : 0);
+        if (k < 2) {
+            c.buffer = 0;
+            int v = clampi(f2i(rintf(vy)), 0, H - 1); // Mathf.RoundToInt, half-to-even
+            c.pix_min = k == 0 ? v : 0;
+            c.pix_max = k == 0 ? H - 1 : v;
+        } else {
+            c.buffer = 1;
+            int v = clampi(f2i(rintf(vx)), 0, W - 1);
+            c.pix_min = k == 3 ? 0 : v;
+            c.pix_max = k == 3 ? v : W - 1;
+        }
+    }
+    return total;
+}
+
+int validate_setup(cvx_ctx* ctx, const cvx_frame_setup* s, int total) {
+    const int W = ctx->width, H = ctx->height;
+    int tdRays = (s->segments[0].ray_count > 0 ? s->segments[0].ray_count : 0) + (s->segments[1].ray_count > 0 ? s->segments[1].ray_count : 0);
+    int lrRays = (s->segments[2].ray_count > 0 ? s->segments[2].ray_count : 0) + (s->segments[3].ray_count > 0 ? s->segments[3].ray_count : 0);
+    if (tdRays > W + 2 * H || lrRays > 2 * W + H)
+        return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "segment ray counts (%d top/down, %d left/right) exceed the raybuffers (%d, %d rows)", tdRays, lrRays, W + 2 * H, 2 * W + H);
+    (void)total;
+    return CVX_OK;
+}
+
+void make_frame(cvx_ctx* ctx, const cvx_frame_setup* s, cvxd_frame& f) {
+    memset(&f, 0, sizeof f);
+    memcpy(f.wts, s->camera.world_to_screen, sizeof f.wts);
+    f.pos_x = s->camera.position_xz[0]; f.pos_z = s->camera.position_xz[1]; f.pos_y = s->camera.position_y;
+    f.inverse = s->camera.inverse_element_iteration_direction ? 1 : 0;
+    f.far_clip = s->camera.far_clip;
+    memcpy(f.lod_dist, s->camera.lod_distances, sizeof f.lod_dist);
+    f.total_rays = fill_segments(s, ctx->width, ctx->height, f.seg);
+    f.vp_x = s->vanishing_point_screen[0]; f.vp_y = s->vanishing_point_screen[1];
+    f.width = ctx->width; f.height = ctx->height;
+    f.ray_begin = 0; f.ray_end = f.total_rays;
+    f.td = ctx->td; f.lr = ctx->lr;
+    f.counters = (ctx->flags & CVX_FLAG_COUNTERS) ? ctx->counters : nullptr;
+}
+
+void make_blit(cvx_ctx* ctx, const cvxd_frame& f, uint32_t* target, cvxd_blit& b) {
+    memset(&b, 0, sizeof b);
+    memcpy(b.seg, f.seg, sizeof b.seg);
+    b.vp_x = f.vp_x; b.vp_y = f.vp_y;
+    b.width = ctx->width; b.height = ctx->height;
+    b.row_begin = 0; b.row_end = ctx->height;
+    b.ray_begin = 0; b.ray_end = f.total_rays; b.owned_only = 0;
+    b.td = ctx->td; b.lr = ctx->lr;
+    b.frame = target;
+}
+
+int check_ready(cvx_ctx* ctx, const void* setup) {
+    if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
+    if (!setup) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "frame setup is NULL");
+    if (ctx->world.lod_count <= 0 || !ctx->world.lods[0].headers) return fail(ctx, CVX_ERR_NO_WORLD, "no world uploaded (LOD 0 missing)");
+    if (ctx->width <= 0) return fail(ctx, CVX_ERR_NO_RESOLUTION, "cvx_set_resolution has not been called");
+    return CVX_OK;
+}
+
+uint32_t* current_target(cvx_ctx* ctx) { return ctx->externalFrame ? ctx->externalFrame : ctx->frames[ctx->frameIndex]; }
+
+void free_resolution(cvx_ctx* ctx) {
+    cudaFree(ctx->td); cudaFree(ctx->lr); cudaFree(ctx->frames[0]); cudaFree(ctx->frames[1]);
+    ctx->td = ctx->lr = ctx->frames[0] = ctx->frames[1] = nullptr;
+    ctx->width = ctx->height = 0;
+}
+
+void free_world(cvx_ctx* ctx) {
+    for (int i = 0; i < CVX_LOD_LEVELS; i++) {
+        cudaFree(ctx->lodHeaders[i]); cudaFree(ctx->lodElements[i]);
+        ctx->lodHeaders[i] = ctx->lodElements[i] = nullptr;
+    }
+    memset(&ctx->world, 0, sizeof ctx->world);
+}
+
+} // namespace
+
+extern "C" {
+
+int cvx_create(const cvx_config* config, cvx_ctx** out_ctx) {
+    if (!out_ctx) return fail(nullptr, CVX_ERR_INVALID_ARGUMENT, "out_ctx is NULL");
+    *out_ctx = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return fail(nullptr, CVX_ERR_NO_DEVICE, "no CUDA device (%s); libcpuvox_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count = 0");
+    int dev = config ? config->device : 0;
+    if (dev < 0 || dev >= count) return fail(nullptr, CVX_ERR_INVALID_ARGUMENT, "device %d out of range (%d devices)", dev, count);
+    cvx_ctx* ctx = new (std::nothrow) cvx_ctx();
+    if (!ctx) return fail(nullptr, CVX_ERR_OUT_OF_MEMORY, "out of host memory");
+    ctx->device = dev;
+    ctx->flags = config ? config->flags : 0;
+    memset(&ctx->world, 0, sizeof ctx->world);
+    memset(ctx->lodHeaders, 0, sizeof ctx->lodHeaders);
+    memset(ctx->lodElements, 0, sizeof ctx->lodElements);
+#define CREATE_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(nullptr, CVX_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); cvx_destroy(ctx); return CVX_ERR_CUDA; } } while (0)
+    CREATE_CU(cudaSetDevice(dev));
+    CREATE_CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CREATE_CU(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+    CREATE_CU(cudaEventCreate(&ctx->evStart));
+    CREATE_CU(cudaEventCreate(&ctx->evMid));
+    CREATE_CU(cudaEventCreate(&ctx->evEnd));
+    for (int i = 0; i < 2; i++) {
+        CREATE_CU(cudaEventCreateWithFlags(&ctx->evFrameDone[i], cudaEventDisableTiming));
+        CREATE_CU(cudaEventCreateWithFlags(&ctx->evCopyDone[i], cudaEventDisableTiming));
+    }
+    CREATE_CU(cudaMalloc(&ctx->counters, sizeof(cvxd_counters)));
+    CREATE_CU(cudaMemset(ctx->counters, 0, sizeof(cvxd_counters)));
+#undef CREATE_CU
+    *out_ctx = ctx;
+    return CVX_OK;
+}
+
+int cvx_destroy(cvx_ctx* ctx) {
+    if (!ctx) return CVX_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copyStream) cudaStreamSynchronize(ctx->copyStream);
+    free_resolution(ctx);
+    free_world(ctx);
+    cudaFree(ctx->counters);
+    if (ctx->evStart) cudaEventDestroy(ctx->evStart);
+    if (ctx->evMid) cudaEventDestroy(ctx->evMid);
+    if (ctx->evEnd) cudaEventDestroy(ctx->evEnd);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->evFrameDone[i]) cudaEventDestroy(ctx->evFrameDone[i]);
+        if (ctx->evCopyDone[i]) cudaEventDestroy(ctx->evCopyDone[i]);
+    }
+    if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
+    delete ctx;
+    return CVX_OK;
+}
+
+const char* cvx_last_error(const cvx_ctx* ctx) { return ctx ? ctx->error.c_str() : g_createError.c_str(); }
+
+int cvx_set_stream(cvx_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
+    if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->ownStream = false; }
+    else { CU(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->ownStream = true; }
+    return CVX_OK;
+}
+
+int cvx_world_upload(cvx_ctx* ctx, int32_t lod, int32_t dim_x, int32_t dim_y, int32_t dim_z, const void* blob, int64_t bytes, int32_t column_count) {
+    if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
+    auto pow2 = [](int n) { return n > 0 && (n & (n - 1)) == 0; };
+    if (lod < 0 || lod >= CVX_LOD_LEVELS || !blob) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "bad lod %d or NULL blob", lod);
+    if (!pow2(dim_x) || !pow2(dim_z) || dim_y < 1 || dim_y > 32768) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "world dimensions %dx%dx%d: x/z must be powers of two, y <= 32768", dim_x, dim_y, dim_z);
+    const int64_t needCols = (int64_t)(dim_x >> lod) * (dim_z >> lod);
+    if (needCols < 1 || column_count < needCols) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "column_count %d too small for LOD %d (%lld columns addressed)", column_count, lod, (long long)needCols);
+    const int64_t headerBytes = 12 * (int64_t)column_count;
+    if (bytes < headerBytes || ((bytes - headerBytes) & 3)) return fail(ctx, CVX_ERR_FORMAT, "blob of %lld bytes cannot hold %d column headers", (long long)bytes, column_count);
+    if (ctx->world.lod_count > 0 && (ctx->world.dim_x != dim_x || ctx->world.dim_y != dim_y || ctx->world.dim_z != dim_z))
+        return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "LOD %d dimensions differ from the already uploaded world; call cvx_world_free first", lod);
+    const int64_t elementCells = (bytes - headerBytes) / 4;
+    // validate on the host what the kernels index with: offsets + run counts must stay inside the element area
+    {
+        const uint8_t* p = (const uint8_t*)blob;
+        for (int64_t i = 0; i < needCols; i++) {
+            int32_t off; uint16_t rc;
+            memcpy(&off, p + 12 * i, 4); memcpy(&rc, p + 12 * i + 4, 2);
+            if (rc == 0) continue;
+            if (off < 0 || (int64_t)off + rc + 2 > elementCells) return fail(ctx, CVX_ERR_FORMAT, "column %lld of LOD %d points outside the element area", (long long)i, lod);
+        }
+    }
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->lodHeaders[lod]); cudaFree(ctx->lodElements[lod]);
+    ctx->lodHeaders[lod] = ctx->lodElements[lod] = nullptr;
+    void* staging = nullptr;
+    CU(ctx, cudaMalloc(&staging, (size_t)headerBytes));
+    cudaError_t e = cudaMalloc(&ctx->lodHeaders[lod], (size_t)(16 * needCols));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->lodElements[lod], (size_t)(elementCells > 0 ? 4 * elementCells : 4));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(staging, blob, (size_t)(12 * needCols), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && elementCells > 0) e = cudaMemcpyAsync(ctx->lodElements[lod], (const uint8_t*)blob + headerBytes, (size_t)(4 * elementCells), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) { e = cvxd_launch_transcode_headers((const uint8_t*)staging, (uint4*)ctx->lodHeaders[lod], (const uint32_t*)ctx->lodElements[lod], needCols, ctx->stream); ctx->launches++; }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(staging);
+    if (e != cudaSuccess) {
+        cudaFree(ctx->lodHeaders[lod]); cudaFree(ctx->lodElements[lod]);
+        ctx->lodHeaders[lod] = ctx->lodElements[lod] = nullptr;
+        return fail(ctx, e == cudaErrorMemoryAllocation ? CVX_ERR_OUT_OF_MEMORY : CVX_ERR_CUDA, "world upload failed: %s", cudaGetErrorString(e));
+    }
+    ctx->world.dim_x = dim_x; ctx->world.dim_y = dim_y; ctx->world.dim_z = dim_z;
+    cvxd_lod& l = ctx->world.lods[lod];
+    l.headers = (const uint4*)ctx->lodHeaders[lod];
+    l.elements = (const uint32_t*)ctx->lodElements[lod];
+    l.mul_x = dim_z >> lod;
+    l.lod = lod;
+    if (lod + 1 > ctx->world.lod_count) ctx->world.lod_count = lod + 1;
+    return CVX_OK;
+}
+
+int cvx_world_free(cvx_ctx* ctx) {
+    if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    free_world(ctx);
+    return CVX_OK;
+}
+
+int cvx_set_resolution(cvx_ctx* ctx, int32_t width, int32_t height) {
+    if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
+    if (width < 1 || height < 1 || width > CVXD_MAX_AXIS || height > CVXD_MAX_AXIS)
+        return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "resolution %dx%d out of range (1..%d)", width, height, CVXD_MAX_AXIS);
+    if (width == ctx->width && height == ctx->height) return CVX_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->copyStream));
+    free_resolution(ctx);
+    const size_t tdBytes = (size_t)height * (size_t)(width + 2 * height) * 4; // RenderManager.cs:36
+    const size_t lrBytes = (size_t)width * (size_t)(2 * width + height) * 4;  // RenderManager.cs:35
+    const size_t fbBytes = (size_t)width * height * 4;
+    cudaError_t e = cudaMalloc(&ctx->td, tdBytes);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->lr, lrBytes);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->frames[0], fbBytes);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->frames[1], fbBytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->td, 0, tdBytes, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->lr, 0, lrBytes, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->frames[0], 0, fbBytes, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->frames[1], 0, fbBytes, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        free_resolution(ctx);
+        return fail(ctx, e == cudaErrorMemoryAllocation ? CVX_ERR_OUT_OF_MEMORY : CVX_ERR_CUDA, "raybuffer allocation failed: %s", cudaGetErrorString(e));
+    }
+    ctx->width = width; ctx->height = height;
+    return CVX_OK;
+}
+
+int cvx_draw_rays(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t ray_begin, int32_t ray_end) {
+    int r = check_ready(ctx, setup);
+    if (r) return r;
+    cvxd_frame f;
+    make_frame(ctx, setup, f);
+    if ((r = validate_setup(ctx, setup, f.total_rays))) return r;
+    if (ray_end < 0 || ray_end > f.total_rays) ray_end = f.total_rays;
+    if (ray_begin < 0) ray_begin = 0;
+    f.ray_begin = ray_begin; f.ray_end = ray_end;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaEventRecord(ctx->evStart, ctx->stream));
+    CU(ctx, cvxd_launch_phase1(ctx->world, f, ctx->stream));
+    if (ray_end > ray_begin) ctx->launches++;
+    CU(ctx, cudaEventRecord(ctx->evMid, ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->evEnd, ctx->stream));
+    ctx->timed = true;
+    return CVX_OK;
+}
+
+int cvx_blit_rows(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t row_begin, int32_t row_end) {
+    int r = check_ready(ctx, setup);
+    if (r) return r;
+    cvxd_frame f;
+    make_frame(ctx, setup, f);
+    cvxd_blit b;
+    make_blit(ctx, f, current_target(ctx), b);
+    if (row_end < 0 || row_end > ctx->height) row_end = ctx->height;
+    if (row_begin < 0) row_begin = 0;
+    b.row_begin = row_begin; b.row_end = row_end;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cvxd_launch_phase2(b, ctx->stream));
+    if (row_end > row_begin) ctx->launches++;
+    return CVX_OK;
+}
+
+int cvx_blit_owned(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t ray_begin, int32_t ray_end, void* device_frame) {
+    int r = check_ready(ctx, setup);
+    if (r) return r;
+    cvxd_frame f;
+    make_frame(ctx, setup, f);
+    cvxd_blit b;
+    make_blit(ctx, f, device_frame ? (uint32_t*)device_frame : current_target(ctx), b);
+    if (ray_end < 0 || ray_end > f.total_rays) ray_end = f.total_rays;
+    if (ray_begin < 0) ray_begin = 0;
+    b.ray_begin = ray_begin; b.ray_end = ray_end; b.owned_only = 1;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cvxd_launch_phase2(b, ctx->stream));
+    ctx->launches++;
+    return CVX_OK;
+}
+
+static int draw_into(cvx_ctx* ctx, const cvx_frame_setup* setup, uint32_t* target, bool timed) {
+    cvxd_frame f;
+    make_frame(ctx, setup, f);
+    int r = validate_setup(ctx, setup, f.total_rays);
+    if (r) return r;
+    cvxd_blit b;
+    make_blit(ctx, f, target, b);
+    if (timed) CU(ctx, cudaEventRecord(ctx->evStart, ctx->stream));
+    CU(ctx, cvxd_launch_phase1(ctx->world, f, ctx->stream));
+    if (f.total_rays > 0) ctx->launches++;
+    if (timed) CU(ctx, cudaEventRecord(ctx->evMid, ctx->stream));
+    CU(ctx, cvxd_launch_phase2(b, ctx->stream));
+    ctx->launches++;
+    if (timed) { CU(ctx, cudaEventRecord(ctx->evEnd, ctx->stream)); ctx->timed = true; }
+    return CVX_OK;
+}
+
+int cvx_draw(cvx_ctx* ctx, const cvx_frame_setup* setup) {
+    int r = check_ready(ctx, setup);
+    if (r) return r;
+    CU(ctx, cudaSetDevice(ctx->device));
+    return draw_into(ctx, setup, current_target(ctx), true);
+}
+
+int cvx_draw_batch(cvx_ctx* ctx, const cvx_frame_setup* setups, int32_t n_views, void* dst_frames) {
+    int r = check_ready(ctx, setups);
+    if (r) return r;
+    if (n_views < 0) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "n_views < 0");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t fbBytes = (size_t)ctx->width * ctx->height * 4;
+    if (!dst_frames) { // device only: frames overwrite each other in the current target
+        for (int i = 0; i < n_views; i++) if ((r = draw_into(ctx, setups + i, current_target(ctx), false))) return r;
+        return CVX_OK;
+    }
+    // pipelined: view i renders into internal buffer i&1 on the compute stream while view i-1 is copied to the host
+    // on the copy stream. The copy is asynchronous only if dst_frames is page-locked (cvx_alloc_pinned / cudaHostRegister).
+    for (int i = 0; i < n_views; i++) {
+        const int slot = i & 1;
+        if (i >= 2) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evCopyDone[slot], 0)); // buffer free again
+        if ((r = draw_into(ctx, setups + i, ctx->frames[slot], false))) return r;
+        CU(ctx, cudaEventRecord(ctx->evFrameDone[slot], ctx->stream));
+        CU(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evFrameDone[slot], 0));
+        CU(ctx, cudaMemcpyAsync((uint8_t*)dst_frames + (size_t)i * fbBytes, ctx->frames[slot], fbBytes, cudaMemcpyDeviceToHost, ctx->copyStream));
+        CU(ctx, cudaEventRecord(ctx->evCopyDone[slot], ctx->copyStream));
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->copyStream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return CVX_OK;
+}
+
+int cvx_sync(cvx_ctx* ctx) {
+    if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->copyStream));
+    return CVX_OK;
+}
+
+int cvx_read_frame(cvx_ctx* ctx, void* dst_argb, int64_t bytes) {
+    if (!ctx || !dst_argb) return CVX_ERR_INVALID_ARGUMENT;
+    if (ctx->width <= 0) return fail(ctx, CVX_ERR_NO_RESOLUTION, "no resolution set");
+    const int64_t need = (int64_t)ctx->width * ctx->height * 4;
+    if (bytes < need) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "destination holds %lld bytes, frame needs %lld", (long long)bytes, (long long)need);
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(dst_argb, current_target(ctx), (size_t)need, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return CVX_OK;
+}
+
+int cvx_read_raybuffer(cvx_ctx* ctx, int32_t which, void* dst_argb, int64_t bytes) {
+    if (!ctx || !dst_argb || which < 0 || which > 1) return CVX_ERR_INVALID_ARGUMENT;
+    if (ctx->width <= 0) return fail(ctx, CVX_ERR_NO_RESOLUTION, "no resolution set");
+    const int64_t W = ctx->width, H = ctx->height;
+    const int64_t full = which == 0 ? H * (W + 2 * H) * 4 : W * (2 * W + H) * 4;
+    const int64_t n = bytes < full ? bytes : full;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(dst_argb, which == 0 ? ctx->td : ctx->lr, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return CVX_OK;
+}
+
+int cvx_clear_raybuffers(cvx_ctx* ctx, uint32_t argb) { // RenderManager.ClearRayBuffer (debug), RenderManager.cs:58-92
+    if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
+    if (ctx->width <= 0) return fail(ctx, CVX_ERR_NO_RESOLUTION, "no resolution set");
+    const int64_t W = ctx->width, H = ctx->height;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cvxd_launch_fill(ctx->td, argb, H * (W + 2 * H), ctx->stream));
+    CU(ctx, cvxd_launch_fill(ctx->lr, argb, W * (2 * W + H), ctx->stream));
+    ctx->launches += 2;
+    return CVX_OK;
+}
+
+int cvx_get_counters(cvx_ctx* ctx, cvx_counters* out, int32_t reset) {
+    if (!ctx || !out) return CVX_ERR_INVALID_ARGUMENT;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(out, ctx->counters, sizeof *out, cudaMemcpyDeviceToHost, ctx->stream));
+    if (reset) CU(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(cvxd_counters), ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return CVX_OK;
+}
+
+int cvx_device_frame(cvx_ctx* ctx, void** out_device_ptr, int64_t* out_bytes) {
+    if (!ctx || !out_device_ptr) return CVX_ERR_INVALID_ARGUMENT;
+    if (ctx->width <= 0) return fail(ctx, CVX_ERR_NO_RESOLUTION, "no resolution set");
+    *out_device_ptr = current_target(ctx);
+    if (out_bytes) *out_bytes = (int64_t)ctx->width * ctx->height * 4;
+    return CVX_OK;
+}
+
+int cvx_device_raybuffer(cvx_ctx* ctx, int32_t which, void** out_device_ptr, int64_t* out_bytes) {
+    if (!ctx || !out_device_ptr || which < 0 || which > 1) return CVX_ERR_INVALID_ARGUMENT;
+    if (ctx->width <= 0) return fail(ctx, CVX_ERR_NO_RESOLUTION, "no resolution set");
+    const int64_t W = ctx->width, H = ctx->height;
+    *out_device_ptr = which == 0 ? ctx->td : ctx->lr;
+    if (out_bytes) *out_bytes = which == 0 ? H * (W + 2 * H) * 4 : W * (2 * W + H) * 4;
+    return CVX_OK;
+}
+
+int cvx_set_external_frame(cvx_ctx* ctx, void* device_ptr) {
+    if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
+    ctx->externalFrame = (uint32_t*)device_ptr;
+    return CVX_OK;
+}
+
+int cvx_last_draw_ms(cvx_ctx* ctx, float* out_phase1_ms, float* out_phase2_ms) {
+    if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
+    if (!ctx->timed) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "no timed draw yet");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaEventSynchronize(ctx->evEnd));
+    float a = 0, b = 0;
+    CU(ctx, cudaEventElapsedTime(&a, ctx->evStart, ctx->evMid));
+    CU(ctx, cudaEventElapsedTime(&b, ctx->evMid, ctx->evEnd));
+    if (out_phase1_ms) *out_phase1_ms = a;
+    if (out_phase2_ms) *out_phase2_ms = b;
+    return CVX_OK;
+}
+
+int64_t cvx_launch_count(const cvx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int cvx_debug_ray_setup(cvx_ctx* ctx, const cvx_frame_setup* setup, cvx_ray_state* out, int32_t max_rays) {
+    int r = check_ready(ctx, setup);
+    if (r) return r;
+    if (!out || max_rays < 0) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "bad output buffer");
+    cvxd_frame f;
+    make_frame(ctx, setup, f);
+    int n = f.total_rays < max_rays ? f.total_rays : max_rays;
+    if (n == 0) return f.total_rays;
+    CU(ctx, cudaSetDevice(ctx->device));
+    cvxd_ray_state* d = nullptr;
+    CU(ctx, cudaMalloc(&d, sizeof(cvxd_ray_state) * (size_t)n));
+    cudaError_t e = cvxd_launch_ray_setup(ctx->world, f, d, n, ctx->stream);
+    ctx->launches++;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, sizeof(cvxd_ray_state) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, CVX_ERR_CUDA, "ray setup dump failed: %s", cudaGetErrorString(e));
+    return f.total_rays;
+}
+
+int cvx_alloc_pinned(int64_t bytes, void** out) {
+    if (!out || bytes <= 0) return CVX_ERR_INVALID_ARGUMENT;
+    cudaError_t e = cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault);
+    return e == cudaSuccess ? CVX_OK : (e == cudaErrorMemoryAllocation ? CVX_ERR_OUT_OF_MEMORY : CVX_ERR_CUDA);
+}
+
+int cvx_free_pinned(void* p) { return cudaFreeHost(p) == cudaSuccess ? CVX_OK : CVX_ERR_CUDA; }
+
+} // extern "C"

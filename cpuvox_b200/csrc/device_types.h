@@ -1,0 +1,90 @@
+/*
+ * device_types.h — plain structs shared by the C-ABI layer (capi.cu) and the kernels (raybuffer_kernels.cu).
+ * Everything here is passed to kernels by value (__grid_constant__), so a frame needs no host->device copy
+ * besides the launch parameters themselves.
+ */
+#pragma once
+#include <stdint.h>
+
+#define CVXD_LODS 6
+#define CVXD_MAX_AXIS 8192          /* longest raybuffer row (max(W,H)) the seen-mask in shared memory supports */
+#define CVXD_SEEN_WORDS (CVXD_MAX_AXIS / 32)
+#define CVXD_WARPS_PER_CTA 4
+
+/* Device copy of one World LOD (Assets/Code/World.cs:8-43,161-188). Headers are transcoded at upload from the
+ * reference's 12-byte RLEColumn into one 16-byte aligned uint4 per column so a lane fetches a column header with
+ * a single 128-bit load:
+ *   x = element offset (in 4-byte cells, relative to `elements`)
+ *   y = runCount | worldMin << 16
+ *   z = worldMax
+ *   w = first RLEElement after the start guard (lets 1-run lookups skip a dependent load; 0 when empty)
+ * `elements` is the reference element area verbatim: [guard][runs...][guard][ColorARGB32...] per column. */
+struct cvxd_lod {
+    const uint4* headers;
+    const uint32_t* elements;
+    int32_t mul_x;      /* dimZ >> lod, World.cs:31 */
+    int32_t lod;
+};
+
+struct cvxd_world {
+    cvxd_lod lods[CVXD_LODS];
+    int32_t dim_x, dim_y, dim_z;
+    int32_t lod_count;
+};
+
+/* DrawSegmentRayJob.SegmentContext (Assets/Code/Rendering/DrawSegmentRayJob.cs:718-727) minus the pointers. */
+struct cvxd_segment {
+    float ray_min[2], ray_max[2];   /* CamLocalPlaneRayMin/Max */
+    float min_screen[2], max_screen[2];
+    int32_t ray_count;
+    int32_t axis_mapped_to_y;
+    int32_t ray_index_offset;
+    int32_t pix_min, pix_max;       /* originalNextFreePixelMin/Max */
+    int32_t buffer;                 /* 0 = top/down, 1 = left/right */
+};
+
+struct cvxd_counters {
+    unsigned long long dda_steps, columns_nonempty, runs_visited, px_voxel, px_sky, rays;
+};
+
+struct cvxd_frame {
+    float wts[16];                  /* CameraData.WorldToScreenMatrix, column-major */
+    float pos_x, pos_z, pos_y;
+    int32_t inverse;                /* InverseElementIterationDirection */
+    float far_clip;
+    float lod_dist[CVXD_LODS];
+    cvxd_segment seg[4];
+    float vp_x, vp_y;
+    int32_t width, height;
+    int32_t total_rays;
+    int32_t ray_begin, ray_end;     /* flat ray indices drawn by this launch (RaySetupJob order) */
+    uint32_t* td;                   /* top/down raybuffer: rows of `height` pixels */
+    uint32_t* lr;                   /* left/right raybuffer: rows of `width` pixels */
+    cvxd_counters* counters;        /* may be null */
+};
+
+struct cvxd_blit {
+    cvxd_segment seg[4];
+    float vp_x, vp_y;
+    int32_t width, height;
+    int32_t row_begin, row_end;     /* screen rows written */
+    int32_t ray_begin, ray_end;     /* only pixels sourced from these flat rays are written when `owned_only` */
+    int32_t owned_only;
+    const uint32_t* td;
+    const uint32_t* lr;
+    uint32_t* frame;
+};
+
+struct cvxd_ray_state { /* mirrors cvx_ray_state */
+    int32_t segment, plane_ray_index, status, lod;
+    int32_t position[2], step[2];
+    float start[2], dir[2], t_delta[2], t_max[2], intersection_distances[2];
+};
+
+#ifdef __CUDACC__
+cudaError_t cvxd_launch_phase1(const cvxd_world& world, const cvxd_frame& frame, cudaStream_t stream);
+cudaError_t cvxd_launch_phase2(const cvxd_blit& blit, cudaStream_t stream);
+cudaError_t cvxd_launch_ray_setup(const cvxd_world& world, const cvxd_frame& frame, cvxd_ray_state* out, int n, cudaStream_t stream);
+cudaError_t cvxd_launch_transcode_headers(const uint8_t* blob_headers12, uint4* out, const uint32_t* elements, int64_t n_columns, cudaStream_t stream);
+cudaError_t cvxd_launch_fill(uint32_t* dst, uint32_t value, int64_t n, cudaStream_t stream);
+#endif

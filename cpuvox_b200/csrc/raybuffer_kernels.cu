@@ -1,0 +1,717 @@
+/*
+ * raybuffer_kernels.cu — sm_100a kernels of the raybuffer renderer.
+ *
+ *   phase1_kernel   one WARP per raybuffer row (ray). Replaces RaySetupJob, DDASetupJob, TraceToFirstColumnJob and
+ *                   RenderJob/ExecuteRay (Assets/Code/Rendering/DrawSegmentRayJob.cs:12-620) in a single launch.
+ *   phase2_kernel   one thread per screen pixel; replaces BlitSegments + RayBufferBlit.shader
+ *                   (Assets/Code/RenderManager.cs:199-256, Assets/Shaders/RayBufferBlit.shader:47-64).
+ *
+ * Design (not a translation of the per-thread C# loop):
+ *  - The DDA cell sequence of a ray (including the LOD switches, SegmentDDAData.cs:31-73,135-150) does not depend on
+ *    world data, so the warp walks it 32 cells ahead: every lane keeps the (uniform) DDA state, lane i captures cell i,
+ *    then all 32 column headers are fetched with one 128-bit load per lane. A ballot picks the non-empty columns; only
+ *    those enter the order-dependent part.
+ *  - Inside a column the RLE runs are spread over lanes: a warp prefix sum gives every run its world-Y bounds, each lane
+ *    projects/clips/rounds its own run's side span and cap span (the float-heavy part, none of which depends on the
+ *    written-pixel state), and the spans are then committed strictly in reference order.
+ *  - The per-row written-pixel set is a bitmask in shared memory (one word per 32 pixels). Pixel loops run 32 pixels
+ *    per step on word-aligned groups (coalesced 128-byte stores), the mask is updated with warp ballots, and the
+ *    "skip already written pixels" scans of ReducePixelHorizon (:660-697) are bit scans.
+ *  - Numerics: IEEE fp32, no FMA contraction (-fmad=false), IEEE division/sqrt, denormals kept (float.Epsilon sentinel
+ *    of :220-221 must survive), same operation order as the reference expressions, so rows match the CPU restatement
+ *    bit for bit.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "device_types.h"
+
+#define FULL_MASK 0xffffffffu
+#define SKYBOX_ARGB 0x191919FFu /* ColorARGB32(25,25,25): bytes a=255,r,g,b (DrawSegmentRayJob.cs:702) */
+
+namespace {
+
+struct F3 { float x, y, z; }; // (screen-axis coordinate, z', w) as kept by SetupProjectedPlaneParams (:642-650)
+
+__device__ __forceinline__ float lerpf(float a, float b, float t) { return a + t * (b - a); }
+__device__ __forceinline__ float unlerpf(float a, float b, float x) { return (x - a) / (b - a); }
+__device__ __forceinline__ F3 lerp3(F3 a, F3 b, float t) { return F3{lerpf(a.x, b.x, t), lerpf(a.y, b.y, t), lerpf(a.z, b.z, t)}; }
+__device__ __forceinline__ float signf(float x) { return (float)((x > 0.0f ? 1 : 0) - (x < 0.0f ? 1 : 0)); }
+__device__ __forceinline__ float minf_(float a, float b) { return a < b ? a : b; }
+__device__ __forceinline__ float maxf_(float a, float b) { return a > b ? a : b; }
+// (int)float as x64 cvttss2si: NaN / out of range -> INT_MIN
+__device__ __forceinline__ int f2i(float f) { return (f >= -2147483648.0f && f < 2147483648.0f) ? (int)f : (int)0x80000000; }
+__device__ __forceinline__ float float_epsilon() { return __int_as_float(1); }
+
+// ---- SegmentDDAData (Assets/Code/Utils/SegmentDDAData.cs) -------------------------------------------------
+struct Dda {
+    int px, pz, sx, sz;
+    float start_x, start_z, dir_x, dir_z, tdx, tdz, tmx, tmz, dl, dn; // dl/dn = IntersectionDistances (last, next)
+};
+
+__device__ __forceinline__ void dda_init(Dda& d, float sx, float sz, float dx, float dz) { // :17-28
+    d.start_x = sx; d.start_z = sz; d.dir_x = dx; d.dir_z = dz;
+    float fx = floorf(sx), fz = floorf(sz);
+    d.px = f2i(fx); d.pz = f2i(fz);
+    d.tdx = 1.0f / maxf_(0.0000001f, fabsf(dx));
+    d.tdz = 1.0f / maxf_(0.0000001f, fabsf(dz));
+    float gx = signf(dx), gz = signf(dz);
+    d.sx = f2i(gx); d.sz = f2i(gz);
+    d.tmx = (gx * -(sx - fx) + (gx * 0.5f) + 0.5f) * d.tdx;
+    d.tmz = (gz * -(sz - fz) + (gz * 0.5f) + 0.5f) * d.tdz;
+    d.dl = maxf_(d.tmx - d.tdx, d.tmz - d.tdz);
+    d.dn = minf_(d.tmx, d.tmz);
+}
+
+__device__ __forceinline__ void dda_next_lod(Dda& d, int voxelSize) { // :31-73
+    int rx = d.px & (voxelSize * 2 - 1), rz = d.pz & (voxelSize * 2 - 1);
+    float prevx = d.tmx - d.tdx, prevz = d.tmz - d.tdz;
+    if ((d.dir_x >= 0.0f) == (rx < voxelSize)) d.tmx += d.tdx; else prevx -= d.tdx;
+    if ((d.dir_z >= 0.0f) == (rz < voxelSize)) d.tmz += d.tdz; else prevz -= d.tdz;
+    d.dl = maxf_(prevx, prevz);
+    d.dn = minf_(d.tmx, d.tmz);
+    d.px -= rx; d.pz -= rz;
+    d.tdx *= 2.0f; d.tdz *= 2.0f;
+    d.sx *= 2; d.sz *= 2;
+}
+
+__device__ __forceinline__ bool dda_step(Dda& d, float farClip) { // :135-150
+    float crossed;
+    if (d.tmx < d.tmz) { crossed = d.tmx; d.tmx += d.tdx; d.px += d.sx; }
+    else               { crossed = d.tmz; d.tmz += d.tdz; d.pz += d.sz; }
+    d.dl = crossed;
+    d.dn = minf_(d.tmx, d.tmz);
+    return crossed >= farClip;
+}
+
+__device__ bool dda_step_to_world(Dda& d, float dimX, float dimZ) { // StepToWorldIntersection :75-130
+    const float ninf = __int_as_float(0xff800000), pinf = __int_as_float(0x7f800000);
+    float ix = 1.0f / d.dir_x, iz = 1.0f / d.dir_z;
+    float tminx = ninf, tminz = ninf, tmaxx = pinf, tmaxz = pinf;
+    if (d.dir_x != 0.0f) {
+        float t1 = -d.start_x * ix, t2 = (dimX - d.start_x) * ix;
+        tminx = minf_(t1, t2); tmaxx = maxf_(t1, t2);
+    }
+    if (d.dir_z != 0.0f) {
+        float t1 = -d.start_z * iz, t2 = (dimZ - d.start_z) * iz;
+        tminz = minf_(t1, t2); tmaxz = maxf_(t1, t2);
+    }
+    float tmint = maxf_(tminx, tminz), tmaxt = minf_(tmaxx, tmaxz);
+    if (tmaxt < tmint || tmint <= 0.0f) return false;
+    float lastx, lastz;
+    if (tminx < tminz && tminx != ninf) {
+        lastz = tminz;
+        float off = tmint * d.dir_x;
+        float hit = d.start_x + off;
+        hit = d.dir_x > 0.0f ? floorf(hit) : ceilf(hit);
+        off = hit - d.start_x;
+        lastx = off / d.dir_x;
+    } else {
+        lastx = tminx;
+        float off = tmint * d.dir_z;
+        float hit = d.start_z + off;
+        hit = d.dir_z > 0.0f ? floorf(hit) : ceilf(hit);
+        off = hit - d.start_z;
+        lastz = off / d.dir_z;
+    }
+    d.tmx = lastx + d.tdx; d.tmz = lastz + d.tdz;
+    d.dl = maxf_(lastx, lastz);
+    d.dn = minf_(d.tmx, d.tmz);
+    float mid = lerpf(d.dl, d.dn, 0.5f);
+    d.px = f2i(floorf(d.start_x + mid * d.dir_x));
+    d.pz = f2i(floorf(d.start_z + mid * d.dir_z));
+    return true;
+}
+
+// ---- CameraData clip helpers (Assets/Code/Utils/CameraData.cs:50-157) --------------------------------------
+__device__ __forceinline__ float cross2(float ax, float ay, float bx, float by) { return ax * by - ay * bx; }
+__device__ __forceinline__ float clip_min(F3 pMin, F3 pMax, float frustum) { // :101-107
+    float fi = 1.0f / frustum;
+    float c0 = cross2(1.0f, fi, pMax.x, pMax.z);
+    float c1 = cross2(1.0f, fi, pMin.x, pMin.z);
+    return 1.0f - (c0 / (c0 - c1));
+}
+__device__ __forceinline__ float clip_max(F3 pMin, F3 pMax, float frustum) { // :109-115
+    float fi = 1.0f / frustum;
+    float c0 = cross2(1.0f, fi, pMax.x, pMax.z);
+    float c1 = cross2(1.0f, fi, pMin.x, pMin.z);
+    return c1 / (c1 - c0);
+}
+__device__ bool world_bounds_clipping(F3 pMin, F3 pMax, float bMin, float bMax, float& minLerp, float& maxLerp) { // :50-99
+    minLerp = 0.0f; maxLerp = 1.0f;
+    if (pMin.x > pMin.z * bMax) {
+        if (pMax.x > pMax.z * bMax) return true;
+        minLerp = clip_min(pMin, pMax, bMax);
+        if (pMax.x < pMax.z * bMin) maxLerp = clip_max(pMin, pMax, bMin);
+    } else if (pMax.x > pMax.z * bMax) {
+        maxLerp = clip_max(pMin, pMax, bMax);
+        if (pMin.x < pMin.z * bMin) minLerp = clip_min(pMin, pMax, bMin);
+    } else if (pMin.x < pMin.z * bMin) {
+        if (pMax.x < pMax.z * bMin) return true;
+        minLerp = clip_min(pMin, pMax, bMin);
+    } else if (pMax.x < pMax.z * bMin) {
+        maxLerp = clip_max(pMin, pMax, bMin);
+    }
+    return false;
+}
+__device__ __forceinline__ bool clip_near(F3& a, F3& b) { // :123-137, near plane z' <= 0 (F3.y)
+    if (a.y <= 0.0f) {
+        if (b.y <= 0.0f) return false;
+        float v = b.y / (b.y - a.y);
+        a = lerp3(b, a, v);
+    } else if (b.y <= 0.0f) {
+        float v = a.y / (a.y - b.y);
+        b = lerp3(a, b, v);
+    }
+    return true;
+}
+__device__ __forceinline__ bool clip_near_u(F3& a, F3& b, float& uA, float& uB) { // :140-157
+    if (a.y <= 0.0f) {
+        if (b.y <= 0.0f) return false;
+        float v = b.y / (b.y - a.y);
+        a = lerp3(b, a, v);
+        uA = lerpf(uB, uA, v);
+    } else if (b.y <= 0.0f) {
+        float v = a.y / (a.y - b.y);
+        b = lerp3(a, b, v);
+        uB = lerpf(uA, uB, v);
+    }
+    return true;
+}
+
+// mul(WorldToScreenMatrix, (x,y,z,w)) with the float4x4 column order, summed left to right
+__device__ __forceinline__ void project(const float* m, float x, float y, float z, float w, float out[4]) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) out[r] = m[r] * x + m[4 + r] * y + m[8 + r] * z + m[12 + r] * w;
+}
+
+// ---- per-ray setup: RaySetupJob :12-40, DDASetupJob :49-77, TraceToFirstColumnJob :87-144 -----------------
+struct RaySetup {
+    int segment, plane_index, lod, status; // status 0 = continue into ExecuteRay, 1 = skybox the whole row, -1 = no such ray
+    int lod_steps;                         // NextLOD iterations of :123-128 (counted as dda_steps)
+    Dda dda;
+};
+
+__device__ void setup_ray(const cvxd_world& world, const cvxd_frame& f, int flatIndex, RaySetup& rs) {
+    int planeIndex = flatIndex, seg = -1;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int n = f.seg[j].ray_count;
+        if (seg >= 0 || n <= 0) continue;
+        if (planeIndex >= n) { planeIndex -= n; continue; }
+        seg = j;
+    }
+    rs.segment = seg; rs.plane_index = planeIndex; rs.lod = 0; rs.lod_steps = 0; rs.status = -1;
+    if (seg < 0) return;
+    const cvxd_segment& sg = f.seg[seg];
+    float t = planeIndex / (float)sg.ray_count;
+    float dx = lerpf(sg.ray_min[0], sg.ray_max[0], t), dz = lerpf(sg.ray_min[1], sg.ray_max[1], t);
+    float inv = 1.0f / sqrtf(dx * dx + dz * dz); // normalize(v) = v * rsqrt(dot(v,v)), rsqrt = 1/sqrt
+    dda_init(rs.dda, f.pos_x, f.pos_z, dx * inv, dz * inv);
+    rs.status = 0;
+    if (rs.dda.px < 0 || rs.dda.pz < 0 || rs.dda.px >= world.dim_x || rs.dda.pz >= world.dim_z) {
+        rs.status = 1;
+        if (dda_step_to_world(rs.dda, (float)world.dim_x, (float)world.dim_z)) {
+            float lodMax = f.lod_dist[0];
+            while (rs.dda.dl >= lodMax) {
+                dda_next_lod(rs.dda, 1 << rs.lod);
+                rs.lod++;
+                rs.lod_steps++;
+                lodMax = f.lod_dist[rs.lod];
+            }
+            if (!(minf_(rs.dda.tmx, rs.dda.tmz) >= f.far_clip)) rs.status = 0; // IsBeyondFarClip :152-155
+        }
+    }
+}
+
+// ---- written-pixel bitmask helpers -------------------------------------------------------------------------
+// first index >= start whose bit is clear, at most limit+1  ("while (i <= limit && seen[i]) i++")
+__device__ __forceinline__ int scan_up(const uint32_t* seen, int start, int limit) {
+    int i = start;
+    while (i <= limit) {
+        uint32_t w = ~seen[i >> 5] & (FULL_MASK << (i & 31));
+        if (w) { int j = (i & ~31) + __ffs(w) - 1; return j <= limit ? j : limit + 1; }
+        i = (i & ~31) + 32;
+    }
+    return limit + 1 > start ? limit + 1 : start;
+}
+// last index <= start whose bit is clear, at least limit-1  ("while (i >= limit && seen[i]) i--")
+__device__ __forceinline__ int scan_down(const uint32_t* seen, int start, int limit) {
+    int i = start;
+    while (i >= limit) {
+        uint32_t w = ~seen[i >> 5] & (FULL_MASK >> (31 - (i & 31)));
+        if (w) { int j = (i & ~31) + 31 - __clz(w); return j >= limit ? j : limit - 1; }
+        i = (i & ~31) - 1;
+    }
+    return limit - 1 < start ? limit - 1 : start;
+}
+
+struct RowState {
+    uint32_t* seen;         // shared-memory bitmask of this row
+    uint32_t* row;          // raybuffer row
+    int orig_min, orig_max; // originalNextFreePixelMin/Max
+    int nf_min, nf_max;     // nextFreePixelMin/Max
+    float fb_min, fb_max;   // frustumBoundsMin/Max
+};
+
+// ReducePixelHorizon :660-697 (uniform across the warp)
+__device__ __forceinline__ void reduce_pixel_horizon(RowState& rw, int& bMin, int& bMax) {
+    if (bMin <= rw.nf_min) {
+        bMin = rw.nf_min;
+        if (bMax >= rw.nf_min) {
+            rw.nf_min = scan_up(rw.seen, bMax + 1, rw.orig_max);
+            rw.fb_min = rw.nf_min - 0.501f;
+        }
+    }
+    if (bMax >= rw.nf_max) {
+        bMax = rw.nf_max;
+        if (bMin <= rw.nf_max) {
+            rw.nf_max = scan_down(rw.seen, bMin - 1, rw.orig_min);
+            rw.fb_max = rw.nf_max + 0.501f;
+        }
+    }
+}
+
+// WriteSkybox :699-708 — every still-unwritten pixel of the row's range, 32 pixels per step
+__device__ __forceinline__ int sky_fill(const RowState& rw, int lane) {
+    int written = 0;
+    for (int w = rw.orig_min >> 5; w <= rw.orig_max >> 5; w++) {
+        int y = (w << 5) + lane;
+        bool put = y >= rw.orig_min && y <= rw.orig_max && !((rw.seen[w] >> lane) & 1u);
+        if (put) rw.row[y] = SKYBOX_ARGB;
+        written += __popc(__ballot_sync(FULL_MASK, put));
+    }
+    return written;
+}
+// WriteSkyboxFull :710-716
+__device__ __forceinline__ int sky_fill_all(uint32_t* row, int mn, int mx, int lane) {
+    for (int y = mn + lane; y <= mx; y += 32) row[y] = SKYBOX_ARGB;
+    return mx >= mn ? mx - mn + 1 : 0;
+}
+
+struct Acc { unsigned long long dda_steps, columns_nonempty, runs_visited, px_voxel, px_sky; };
+
+__global__ void __launch_bounds__(CVXD_WARPS_PER_CTA * 32)
+phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ cvxd_frame f) {
+    __shared__ uint32_t seen_all[CVXD_WARPS_PER_CTA][CVXD_SEEN_WORDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int flat = f.ray_begin + blockIdx.x * CVXD_WARPS_PER_CTA + warp;
+    if (flat >= f.ray_end) return;
+
+    RaySetup rs;
+    setup_ray(world, f, flat, rs);
+    if (rs.status < 0) return;
+    const cvxd_segment& sg = f.seg[rs.segment];
+    const int rowLen = sg.buffer == 0 ? f.height : f.width;
+    uint32_t* row = (sg.buffer == 0 ? f.td : f.lr) + (int64_t)(rs.plane_index + sg.ray_index_offset) * rowLen;
+
+    Acc acc = {(unsigned long long)rs.lod_steps, 0, 0, 0, 0};
+    RowState rw;
+    rw.seen = seen_all[warp];
+    rw.row = row;
+    rw.orig_min = sg.pix_min; rw.orig_max = sg.pix_max;
+    rw.nf_min = rw.orig_min; rw.nf_max = rw.orig_max;
+    rw.fb_min = rw.nf_min - 0.501f; rw.fb_max = rw.nf_max + 0.501f;
+
+    if (rs.status == 1) {
+        acc.px_sky += sky_fill_all(row, rw.orig_min, rw.orig_max, lane);
+    } else {
+        for (int w = lane; w < ((rowLen + 31) >> 5); w += 32) rw.seen[w] = 0u; // stackalloc, zero-initialised (:208)
+        __syncwarp();
+
+        Dda ray = rs.dda;
+        int lod = rs.lod;
+        int voxelScale = 1 << lod;
+        const float farClip = f.far_clip;
+        float lodMax = f.lod_dist[lod];
+        const float worldMaxY = (float)world.dim_y;
+        const float camY = f.pos_y;
+        const float cameraPosYNormalized = camY / worldMaxY;
+        const int ITER = f.inverse ? -1 : 1; // RenderJob.Execute :174-178
+        const float EPS = float_epsilon();
+        float frustumDirMaxWorld = EPS, frustumDirMinWorld = EPS;
+
+        // SetupProjectedPlaneParams :622-651
+        F3 planeBottom, planeTop, planeDir;
+        {
+            float top[4], bot[4], dir[4];
+            project(f.wts, ray.start_x, worldMaxY, ray.start_z, 1.0f, top);
+            project(f.wts, ray.start_x, 0.0f, ray.start_z, 1.0f, bot);
+            project(f.wts, ray.dir_x, 0.0f, ray.dir_z, 0.0f, dir);
+            const int a = sg.axis_mapped_to_y ? 1 : 0;
+            planeBottom = F3{bot[a], bot[2], bot[3]};
+            planeTop = F3{top[a], top[2], top[3]};
+            planeDir = F3{dir[a], dir[2], dir[3]};
+        }
+        const int maskX = world.dim_x - 1, maskZ = world.dim_z - 1;
+
+        bool terminated = false; // ray ended inside the loop: skybox the rest and stop
+        bool reachedEnd = false; // far clip or world exit
+        while (!terminated && !reachedEnd) {
+            // ---- look ahead: up to 32 cells of the DDA, lane i keeps cell i ------------------------------------
+            int n = 0, endKind = 0; // 1 = next cell is outside the world, 2 = far clip crossed after the last cell
+            int myLod = 0, myIdx = 0; float myDl = 0.0f, myDn = 0.0f;
+            for (int i = 0; i < 32; i++) {
+                if (ray.dl >= lodMax) { // :237-243
+                    dda_next_lod(ray, voxelScale);
+                    lod++; voxelScale *= 2;
+                    lodMax = f.lod_dist[lod];
+                }
+                if (((ray.px & maskX) != ray.px) || ((ray.pz & maskZ) != ray.pz)) { endKind = 1; break; } // World.cs:135-138
+                if (lane == i) {
+                    myLod = lod; myDl = ray.dl; myDn = ray.dn;
+                    myIdx = (ray.px >> lod) * world.lods[lod].mul_x + (ray.pz >> lod); // GetIndexKnownInBounds World.cs:145-149
+                }
+                n = i + 1;
+                if (dda_step(ray, farClip)) { endKind = 2; break; }
+            }
+            uint4 hdr = make_uint4(0, 0, 0, 0);
+            if (lane < n) hdr = __ldg(world.lods[myLod].headers + myIdx);
+            uint32_t nonEmpty = __ballot_sync(FULL_MASK, (hdr.y & 0xffffu) != 0u);
+            int cellsDone = n + (endKind == 1 ? 1 : 0); // the out-of-world probe counts as a step
+
+            while (nonEmpty) {
+                const int c = __ffs(nonEmpty) - 1;
+                nonEmpty &= nonEmpty - 1;
+                const float distLast = __shfl_sync(FULL_MASK, myDl, c);
+                const float distNext = __shfl_sync(FULL_MASK, myDn, c);
+                const int cLod = __shfl_sync(FULL_MASK, myLod, c);
+                const uint32_t hOff = __shfl_sync(FULL_MASK, hdr.x, c);
+                const uint32_t hY = __shfl_sync(FULL_MASK, hdr.y, c);
+                const uint32_t hZ = __shfl_sync(FULL_MASK, hdr.z, c);
+                const int runCount = (int)(hY & 0xffffu);
+                const float colWorldMin = (float)(hY >> 16), colWorldMax = (float)(hZ & 0xffffu);
+                const int cScale = 1 << cLod;
+                acc.columns_nonempty++;
+
+                float worldBoundsMin = 0.0f, worldBoundsMax = worldMaxY;
+                if (frustumDirMaxWorld != EPS) { // :261-281
+                    float distTop = frustumDirMaxWorld > 0.0f ? distNext : distLast;
+                    float distBot = frustumDirMinWorld < 0.0f ? distNext : distLast;
+                    float newMax = camY + frustumDirMaxWorld * distTop;
+                    float newMin = camY + frustumDirMinWorld * distBot;
+                    if (newMin > worldBoundsMax || newMax < worldBoundsMin) { terminated = true; cellsDone = c + 1; break; }
+                    if (colWorldMin > newMax || colWorldMax < newMin) continue;
+                    worldBoundsMin = newMin; worldBoundsMax = newMax;
+                }
+
+                // :289-293
+                const F3 minLast = F3{planeBottom.x + planeDir.x * distLast, planeBottom.y + planeDir.y * distLast, planeBottom.z + planeDir.z * distLast};
+                const F3 minNext = F3{planeBottom.x + planeDir.x * distNext, planeBottom.y + planeDir.y * distNext, planeBottom.z + planeDir.z * distNext};
+                const F3 maxLast = F3{planeTop.x + planeDir.x * distLast, planeTop.y + planeDir.y * distLast, planeTop.z + planeDir.z * distLast};
+                const F3 maxNext = F3{planeTop.x + planeDir.x * distNext, planeTop.y + planeDir.y * distNext, planeTop.z + planeDir.z * distNext};
+
+                if (distLast > 2.0f && frustumDirMaxWorld == EPS) { // re-narrow the frustum :295-422
+                    float lastMinL, lastMaxL, nextMinL, nextMaxL;
+                    bool clippedLast = world_bounds_clipping(minLast, maxLast, rw.fb_min, rw.fb_max, lastMinL, lastMaxL);
+                    bool clippedNext = world_bounds_clipping(minNext, maxNext, rw.fb_min, rw.fb_max, nextMinL, nextMaxL);
+                    float clippedMin, clippedMax;
+                    if (clippedLast) {
+                        if (clippedNext) { terminated = true; cellsDone = c + 1; break; }
+                        worldBoundsMin = lerpf(0.0f, worldMaxY, nextMinL);
+                        worldBoundsMax = lerpf(0.0f, worldMaxY, nextMaxL);
+                        frustumDirMaxWorld = (worldBoundsMax - camY) / distNext;
+                        frustumDirMinWorld = (worldBoundsMin - camY) / distNext;
+                        F3 a = lerp3(minNext, maxNext, nextMinL), b = lerp3(minNext, maxNext, nextMaxL);
+                        clippedMin = a.x / a.z; clippedMax = b.x / b.z;
+                        if (clippedMax < clippedMin) { float t = clippedMin; clippedMin = clippedMax; clippedMax = t; }
+                    } else if (clippedNext) {
+                        worldBoundsMin = lerpf(0.0f, worldMaxY, lastMinL);
+                        worldBoundsMax = lerpf(0.0f, worldMaxY, lastMaxL);
+                        F3 a = lerp3(minLast, maxLast, lastMinL), b = lerp3(minLast, maxLast, lastMaxL);
+                        frustumDirMaxWorld = (worldBoundsMax - camY) / distLast;
+                        frustumDirMinWorld = (worldBoundsMin - camY) / distLast;
+                        clippedMin = a.x / a.z; clippedMax = b.x / b.z;
+                        if (clippedMax < clippedMin) { float t = clippedMin; clippedMin = clippedMax; clippedMax = t; }
+                    } else {
+                        if (lastMinL < nextMinL) {
+                            worldBoundsMin = lerpf(0.0f, worldMaxY, lastMinL);
+                            frustumDirMinWorld = (worldBoundsMin - camY) / distLast;
+                        } else {
+                            worldBoundsMin = lerpf(0.0f, worldMaxY, nextMinL);
+                            frustumDirMinWorld = (worldBoundsMin - camY) / distNext;
+                        }
+                        if (lastMaxL > nextMaxL) {
+                            worldBoundsMax = lerpf(0.0f, worldMaxY, lastMaxL);
+                            frustumDirMaxWorld = (worldBoundsMax - camY) / distLast;
+                        } else {
+                            worldBoundsMax = lerpf(0.0f, worldMaxY, nextMaxL);
+                            frustumDirMaxWorld = (worldBoundsMax - camY) / distNext;
+                        }
+                        F3 aA = lerp3(minLast, maxLast, lastMinL), bA = lerp3(minLast, maxLast, lastMaxL);
+                        F3 aB = lerp3(minNext, maxNext, nextMinL), bB = lerp3(minNext, maxNext, nextMaxL);
+                        float mnN = aB.x / aB.z, mnL = aA.x / aA.z, mxN = bB.x / bB.z, mxL = bA.x / bA.z;
+                        if (mxN < mnN) { float t = mxN; mxN = mnN; mnN = t; }
+                        if (mxL < mnL) { float t = mxL; mxL = mnL; mnL = t; }
+                        clippedMin = minf_(mnL, mnN);
+                        clippedMax = maxf_(mxL, mxN);
+                    }
+                    worldBoundsMin = floorf(worldBoundsMin);
+                    worldBoundsMax = ceilf(worldBoundsMax);
+                    int writableMin = f2i(floorf(clippedMin));
+                    int writableMax = f2i(ceilf(clippedMax));
+                    if (writableMax < rw.nf_min || writableMin > rw.nf_max) { terminated = true; cellsDone = c + 1; break; }
+                    if (writableMin > rw.nf_min) rw.nf_min = scan_up(rw.seen, writableMin, rw.orig_max);
+                    if (writableMax < rw.nf_max) rw.nf_max = scan_down(rw.seen, writableMax, rw.orig_min);
+                    if (rw.nf_min > rw.nf_max) { terminated = true; cellsDone = c + 1; break; }
+                }
+
+                // ---- runs of this column, 32 per pass, in iteration order (:424-611) ---------------------------
+                const uint32_t* colBase = world.lods[cLod].elements + hOff;   // ElementGuardStart World.cs:175-178
+                const uint32_t* colColors = colBase + runCount + 2;           // ColorPointer :185-188
+                int chunkStartY = ITER > 0 ? world.dim_y : 0;                 // running elementBounds, exact in int
+                bool colStop = false;
+                for (int k0 = 0; k0 < runCount && !colStop && !terminated; k0 += 32) {
+                    const int k = k0 + lane;
+                    const bool inCol = k < runCount;
+                    uint32_t el = inCol ? __ldg(colBase + (ITER > 0 ? 1 + k : runCount - k)) : 0u;
+                    const int ci = (int)(short)(el & 0xffffu), len = (int)(short)(el >> 16); // RLEElement World.cs:245-259
+                    // an invalid element (Length == 0) ends the column (:445-447)
+                    const uint32_t invalidMask = __ballot_sync(FULL_MASK, inCol && len == 0) | (runCount - k0 >= 32 ? 0u : (FULL_MASK << (runCount - k0)));
+                    const int nValid = invalidMask ? __ffs(invalidMask) - 1 : 32;
+                    const bool valid = lane < nValid;
+                    int span = valid ? len * cScale : 0;
+                    int incl = span;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += v; }
+                    const int chunkTotal = __shfl_sync(FULL_MASK, incl, 31);
+                    float eMin, eMax; // elementBoundsMin/Max :449-455
+                    if (ITER > 0) { eMax = (float)(chunkStartY - (incl - span)); eMin = (float)(chunkStartY - incl); }
+                    else          { eMin = (float)(chunkStartY + (incl - span)); eMax = (float)(chunkStartY + incl); }
+                    chunkStartY += ITER > 0 ? -chunkTotal : chunkTotal;
+                    if (nValid < 32 && (k0 + nValid) < runCount) colStop = true; // hit an invalid element inside the column
+
+                    const bool solid = valid && ci >= 0; // !IsAir
+                    const bool above = eMin > worldBoundsMax, below = eMax < worldBoundsMin;
+                    const bool isBreak = solid && (ITER > 0 ? (!above && below) : above); // :461-475 (above is tested first)
+                    const uint32_t breakMask = __ballot_sync(FULL_MASK, isBreak);
+                    int nVisit = nValid;
+                    if (breakMask) { nVisit = __ffs(breakMask); colStop = true; } // the breaking run itself was dereferenced
+                    bool active = solid && lane < nVisit && !above && !below;
+
+                    // ---- per-lane span geometry; depends only on column constants ------------------------------
+                    bool sideOk = false, capOk = false;
+                    int sMin = 0, sMax = 0, cMin = 0, cMax = 0, capIdx = 0;
+                    float bfx = 0.0f, bfy = 0.0f, uvAx = 0.0f, uvAy = 0.0f, uvBx = 0.0f, uvBy = 0.0f;
+                    if (active) {
+                        float portionBottom = unlerpf(0.0f, worldMaxY, eMin); // :478-481
+                        float portionTop = unlerpf(0.0f, worldMaxY, eMax);
+                        F3 frontBottom = lerp3(minLast, maxLast, portionBottom);
+                        F3 frontTop = lerp3(minLast, maxLast, portionTop);
+                        float uA = (float)len, uB = 0.0f;
+                        if (clip_near_u(frontBottom, frontTop, uA, uB)) { // :489-502 (clips frontBottom/Top in place)
+                            uvAx = 1.0f / frontBottom.z; uvAy = uA / frontBottom.z;
+                            uvBx = 1.0f / frontTop.z;    uvBy = uB / frontTop.z;
+                            bfx = frontBottom.x / frontBottom.z; bfy = frontTop.x / frontTop.z;
+                            if (bfx > bfy) {
+                                float t = bfx; bfx = bfy; bfy = t;
+                                t = uvAx; uvAx = uvBx; uvBx = t;
+                                t = uvAy; uvAy = uvBy; uvBy = t;
+                            }
+                            sMin = f2i(rintf(bfx)); sMax = f2i(rintf(bfy));
+                            sideOk = true;
+                        }
+                        F3 secA, secB; bool cap = false; // :544-565
+                        if (portionTop < cameraPosYNormalized) {
+                            if (!(eMax > worldBoundsMax)) { cap = true; capIdx = ci; secA = lerp3(minNext, maxNext, portionTop); secB = frontTop; }
+                        } else if (portionBottom > cameraPosYNormalized) {
+                            if (!(eMin < worldBoundsMin)) { cap = true; capIdx = ci + len - 1; secA = lerp3(minNext, maxNext, portionBottom); secB = frontBottom; }
+                        }
+                        if (cap && clip_near(secA, secB)) { // :568-578
+                            cMin = f2i(rintf(secA.x / secA.z)); cMax = f2i(rintf(secB.x / secB.z));
+                            if (cMin > cMax) { int t = cMin; cMin = cMax; cMax = t; }
+                            capOk = true;
+                        }
+                    }
+
+                    // ---- commit spans in reference order --------------------------------------------------------
+                    uint32_t todo = __ballot_sync(FULL_MASK, active && (sideOk || capOk));
+                    int visitedHere = nVisit;
+                    while (todo) {
+                        const int j = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        if (__shfl_sync(FULL_MASK, (int)sideOk, j)) {
+                            int bMin = __shfl_sync(FULL_MASK, sMin, j), bMax = __shfl_sync(FULL_MASK, sMax, j);
+                            if (bMax >= rw.nf_min && bMin <= rw.nf_max) { // :505
+                                reduce_pixel_horizon(rw, bMin, bMax);
+                                const float jbfx = __shfl_sync(FULL_MASK, bfx, j), jbfy = __shfl_sync(FULL_MASK, bfy, j);
+                                const float jAx = __shfl_sync(FULL_MASK, uvAx, j), jAy = __shfl_sync(FULL_MASK, uvAy, j);
+                                const float jBx = __shfl_sync(FULL_MASK, uvBx, j), jBy = __shfl_sync(FULL_MASK, uvBy, j);
+                                const int jLen = __shfl_sync(FULL_MASK, len, j), jCi = __shfl_sync(FULL_MASK, ci, j);
+                                int wrote = 0;
+                                if (bMin <= bMax) {
+                                    for (int w = bMin >> 5; w <= bMax >> 5; w++) { // :519-533
+                                        const int y = (w << 5) + lane;
+                                        const uint32_t sw = rw.seen[w];
+                                        const bool put = y >= bMin && y <= bMax && !((sw >> lane) & 1u);
+                                        if (put) {
+                                            float l = unlerpf(jbfx, jbfy, (float)y);
+                                            float wx = lerpf(jAx, jBx, l), wy = lerpf(jAy, jBy, l);
+                                            float u = wy / wx;
+                                            int idx = max(0, min(jLen - 1, f2i(floorf(u)))) + jCi;
+                                            row[y] = __ldg(colColors + idx);
+                                        }
+                                        const uint32_t pm = __ballot_sync(FULL_MASK, put);
+                                        if (pm) { if (lane == 0) rw.seen[w] = sw | pm; wrote += __popc(pm); }
+                                    }
+                                    __syncwarp();
+                                }
+                                if (wrote) { frustumDirMaxWorld = EPS; acc.px_voxel += wrote; }
+                                if (rw.nf_min > rw.nf_max) { terminated = true; visitedHere = j + 1; break; } // :535-539
+                            }
+                        }
+                        if (__shfl_sync(FULL_MASK, (int)capOk, j)) {
+                            int bMin = __shfl_sync(FULL_MASK, cMin, j), bMax = __shfl_sync(FULL_MASK, cMax, j);
+                            if (bMax >= rw.nf_min && bMin <= rw.nf_max) { // :581
+                                reduce_pixel_horizon(rw, bMin, bMax);
+                                const uint32_t color = __ldg(colColors + __shfl_sync(FULL_MASK, capIdx, j));
+                                int wrote = 0;
+                                if (bMin <= bMax) {
+                                    for (int w = bMin >> 5; w <= bMax >> 5; w++) { // :595-602
+                                        const int y = (w << 5) + lane;
+                                        const uint32_t sw = rw.seen[w];
+                                        const bool put = y >= bMin && y <= bMax && !((sw >> lane) & 1u);
+                                        if (put) row[y] = color;
+                                        const uint32_t pm = __ballot_sync(FULL_MASK, put);
+                                        if (pm) { if (lane == 0) rw.seen[w] = sw | pm; wrote += __popc(pm); }
+                                    }
+                                    __syncwarp();
+                                }
+                                if (wrote) { frustumDirMaxWorld = EPS; acc.px_voxel += wrote; }
+                                if (rw.nf_min > rw.nf_max) { terminated = true; visitedHere = j + 1; break; } // :604-608
+                            }
+                        }
+                    }
+                    acc.runs_visited += visitedHere;
+                }
+                if (terminated) { cellsDone = c + 1; break; }
+            }
+            acc.dda_steps += cellsDone;
+            if (endKind != 0) reachedEnd = true;
+        }
+        acc.px_sky += sky_fill(rw, lane); // :248,268,323,401,419,537,606,619 all end in WriteSkybox
+    }
+
+    if (f.counters && lane == 0) {
+        atomicAdd(&f.counters->dda_steps, acc.dda_steps);
+        atomicAdd(&f.counters->columns_nonempty, acc.columns_nonempty);
+        atomicAdd(&f.counters->runs_visited, acc.runs_visited);
+        atomicAdd(&f.counters->px_voxel, acc.px_voxel);
+        atomicAdd(&f.counters->px_sky, acc.px_sky);
+        atomicAdd(&f.counters->rays, 1ull);
+    }
+}
+
+// ---- Phase 2 -----------------------------------------------------------------------------------------------
+// Per pixel centre (x+0.5, y+0.5), bottom-left origin. Triangle k = (VP, MaxScreen_k, MinScreen_k) carries
+// uv = (0,0),(1,0),(0,1) (RenderManager.cs:215-222), so uv.x / uv.y are the affine weights b / c of Max / Min.
+// The pixel takes the first segment with b >= 0 and c >= 0 (else the one with the largest min(b,c)); the ray row is
+// floor((offset_k + b/(b+c) * scale_k) * bufferRows) (shader :55-56, RenderManager.cs:235-242) clamped to the
+// segment's rows, the column is y (top/down) or x (left/right) (shader :58-62), point sampled.
+__global__ void __launch_bounds__(256)
+phase2_kernel(const __grid_constant__ cvxd_blit p) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = p.row_begin + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= p.width || y >= p.row_end) return;
+    const float px = (float)x + 0.5f, py = (float)y + 0.5f;
+    const float dx = px - p.vp_x, dy = py - p.vp_y;
+    const int tdRows = p.width + 2 * p.height, lrRows = 2 * p.width + p.height;
+    int best = -1; float bestB = 0.0f, bestC = 0.0f, bestScore = __int_as_float(0xff800000);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (p.seg[k].ray_count <= 0 || (best >= 0 && bestB >= 0.0f && bestC >= 0.0f)) continue;
+        float e1x = p.seg[k].max_screen[0] - p.vp_x, e1y = p.seg[k].max_screen[1] - p.vp_y;
+        float e2x = p.seg[k].min_screen[0] - p.vp_x, e2y = p.seg[k].min_screen[1] - p.vp_y;
+        float det = e1x * e2y - e1y * e2x;
+        float b = (dx * e2y - dy * e2x) / det;
+        float c = (e1x * dy - e1y * dx) / det;
+        float score = minf_(b, c);
+        if (b >= 0.0f && c >= 0.0f) { best = k; bestB = b; bestC = c; }
+        else if (score > bestScore) { bestScore = score; best = k; bestB = b; bestC = c; }
+    }
+    uint32_t color = 0u;
+    bool owned = true;
+    if (best >= 0) {
+        const int rc = p.seg[best].ray_count;
+        const int rows = best < 2 ? tdRows : lrRows;
+        const float scale = (float)rc / (float)rows;
+        const int off01 = best == 1 ? p.seg[0].ray_count : (best == 3 ? p.seg[2].ray_count : 0);
+        const float offset = (best == 1 || best == 3) ? (float)off01 / (float)rows : 0.0f;
+        float t = bestB / (bestB + bestC);
+        float v = offset + t * scale;
+        int row = f2i(floorf(v * (float)rows));
+        row = max(off01, min(off01 + rc - 1, row));
+        if (p.owned_only) {
+            int flat = row - off01;
+            for (int k = 0; k < best; k++) flat += max(0, p.seg[k].ray_count);
+            owned = flat >= p.ray_begin && flat < p.ray_end;
+        }
+        if (owned) color = best < 2 ? __ldg(p.td + (int64_t)row * p.height + y) : __ldg(p.lr + (int64_t)row * p.width + x);
+    }
+    if (owned) p.frame[(int64_t)y * p.width + x] = color;
+}
+
+__global__ void ray_setup_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ cvxd_frame f, cvxd_ray_state* out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RaySetup rs;
+    setup_ray(world, f, i, rs);
+    cvxd_ray_state o;
+    o.segment = rs.segment; o.plane_ray_index = rs.plane_index; o.status = rs.status; o.lod = rs.lod;
+    o.position[0] = rs.dda.px; o.position[1] = rs.dda.pz; o.step[0] = rs.dda.sx; o.step[1] = rs.dda.sz;
+    o.start[0] = rs.dda.start_x; o.start[1] = rs.dda.start_z; o.dir[0] = rs.dda.dir_x; o.dir[1] = rs.dda.dir_z;
+    o.t_delta[0] = rs.dda.tdx; o.t_delta[1] = rs.dda.tdz; o.t_max[0] = rs.dda.tmx; o.t_max[1] = rs.dda.tmz;
+    o.intersection_distances[0] = rs.dda.dl; o.intersection_distances[1] = rs.dda.dn;
+    out[i] = o;
+}
+
+// 12-byte RLEColumn {int offset; ushort runCount, worldMin, worldMax; pad} -> uint4 device header
+__global__ void transcode_headers_kernel(const uint32_t* __restrict__ src12, uint4* __restrict__ dst, const uint32_t* __restrict__ elements, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w0 = src12[3 * i], w1 = src12[3 * i + 1], w2 = src12[3 * i + 2];
+    uint32_t runCount = w1 & 0xffffu;
+    uint32_t first = runCount ? elements[(int64_t)(int32_t)w0 + 1] : 0u;
+    dst[i] = make_uint4(w0, w1, w2 & 0xffffu, first);
+}
+
+__global__ void fill_kernel(uint32_t* dst, uint32_t value, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = value;
+}
+
+} // namespace
+
+cudaError_t cvxd_launch_phase1(const cvxd_world& world, const cvxd_frame& frame, cudaStream_t stream) {
+    int n = frame.ray_end - frame.ray_begin;
+    if (n <= 0) return cudaSuccess;
+    int blocks = (n + CVXD_WARPS_PER_CTA - 1) / CVXD_WARPS_PER_CTA;
+    phase1_kernel<<<blocks, CVXD_WARPS_PER_CTA * 32, 0, stream>>>(world, frame);
+    return cudaGetLastError();
+}
+
+cudaError_t cvxd_launch_phase2(const cvxd_blit& blit, cudaStream_t stream) {
+    int rows = blit.row_end - blit.row_begin;
+    if (rows <= 0 || blit.width <= 0) return cudaSuccess;
+    dim3 grid((blit.width + 31) / 32, (rows + 7) / 8);
+    phase2_kernel<<<grid, 256, 0, stream>>>(blit);
+    return cudaGetLastError();
+}
+
+cudaError_t cvxd_launch_ray_setup(const cvxd_world& world, const cvxd_frame& frame, cvxd_ray_state* out, int n, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    ray_setup_kernel<<<(n + 127) / 128, 128, 0, stream>>>(world, frame, out, n);
+    return cudaGetLastError();
+}
+
+cudaError_t cvxd_launch_transcode_headers(const uint8_t* blob_headers12, uint4* out, const uint32_t* elements, int64_t n_columns, cudaStream_t stream) {
+    if (n_columns <= 0) return cudaSuccess;
+    transcode_headers_kernel<<<(unsigned)((n_columns + 255) / 256), 256, 0, stream>>>((const uint32_t*)blob_headers12, out, elements, n_columns);
+    return cudaGetLastError();
+}
+
+cudaError_t cvxd_launch_fill(uint32_t* dst, uint32_t value, int64_t n, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    fill_kernel<<<148 * 8, 256, 0, stream>>>(dst, value, n);
+    return cudaGetLastError();
+}

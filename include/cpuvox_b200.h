@@ -1,0 +1,235 @@
+/*
+ * cpuvox_b200.h — C ABI of libcpuvox_b200.so, the B200-native raybuffer renderer.
+ *
+ * This is the drop-in boundary for the one hot path of pipliz/cpuvox: the body of
+ * RenderManager.DrawSegments (Assets/Code/RenderManager.cs:258-372), the raybuffer
+ * upload/copy (Assets/Code/Rendering/RayBuffer.cs:79-96) and BlitSegments +
+ * RayBufferBlit.shader (RenderManager.cs:199-256, Assets/Shaders/RayBufferBlit.shader:47-64).
+ * The reference has no FFI seam (Phase 1 runs as in-process Burst jobs); each entry point below
+ * cites the reference interface it replaces. A C# host binds these with
+ * [DllImport("cpuvox_b200")] — see INTEGRATION.md.
+ *
+ * Plain C99: fixed-width integers, no bool, no STL, no torch types. Every function returns
+ * CVX_OK (0) or a negative cvx_status; nothing throws or exits across the boundary.
+ * The library has no CPU fallback: without a CUDA device cvx_create fails with CVX_ERR_NO_DEVICE.
+ */
+#ifndef CPUVOX_B200_H
+#define CPUVOX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVX_LOD_LEVELS 6 /* UnityManager.LOD_LEVELS, Assets/Code/UnityManager.cs:42 */
+
+typedef enum cvx_status {
+    CVX_OK = 0,
+    CVX_ERR_INVALID_ARGUMENT = -1,
+    CVX_ERR_NO_DEVICE = -2,
+    CVX_ERR_CUDA = -3,
+    CVX_ERR_OUT_OF_MEMORY = -4,
+    CVX_ERR_NO_WORLD = -5,
+    CVX_ERR_NO_RESOLUTION = -6,
+    CVX_ERR_IO = -7,
+    CVX_ERR_FORMAT = -8
+} cvx_status;
+
+/* ---- blittable per-frame inputs -------------------------------------------------------- */
+
+/* RenderManager.SegmentData, RenderManager.cs:503-510 (36 bytes, sequential layout). */
+typedef struct cvx_segment {
+    float min_screen[2];
+    float max_screen[2];
+    float cam_local_plane_ray_min[2];
+    float cam_local_plane_ray_max[2];
+    int32_t ray_count;
+} cvx_segment;
+
+/* CameraData, Assets/Code/Utils/CameraData.cs:11-36. The matrix is the float4x4
+ * WorldToScreenMatrix stored column after column (c0.xyzw, c1.xyzw, c2.xyzw, c3.xyzw). */
+typedef struct cvx_camera {
+    float world_to_screen[16];
+    float position_xz[2];
+    float position_y;
+    int32_t inverse_element_iteration_direction; /* camera.transform.forward.y >= 0 */
+    float far_clip;
+    float lod_distances[CVX_LOD_LEVELS];
+} cvx_camera;
+
+/* Everything RenderManager.DrawWorld hands to DrawSegments + BlitSegments for one frame
+ * (RenderManager.cs:120-167,179-189). */
+typedef struct cvx_frame_setup {
+    cvx_segment segments[4];
+    cvx_camera camera;
+    float vanishing_point_screen[2];
+} cvx_frame_setup;
+
+/* Work-unit counters, identical for the CPU oracle and the GPU path. */
+typedef struct cvx_counters {
+    uint64_t dda_steps;        /* loop iterations reaching World.GetVoxelColumn (DrawSegmentRayJob.cs:245) + NextLOD iterations of :123-128 */
+    uint64_t columns_nonempty; /* of those, columns with runCount > 0 */
+    uint64_t runs_visited;     /* valid RLEElements dereferenced at :444-447 ("voxel-runs") */
+    uint64_t px_voxel;         /* raybuffer pixels written at :531 and :600 */
+    uint64_t px_sky;           /* raybuffer pixels written at :705 and :714 */
+    uint64_t rays;             /* rays set up (sum of RayCount, or the range drawn) */
+} cvx_counters;
+
+typedef struct cvx_config {
+    int32_t device;            /* CUDA device ordinal */
+    int32_t flags;             /* CVX_FLAG_* */
+} cvx_config;
+
+#define CVX_FLAG_COUNTERS 1    /* accumulate cvx_counters on the device (small cost) */
+
+typedef struct cvx_ctx cvx_ctx;
+
+/* ---- lifetime: new RenderManager() / Destroy(), RenderManager.cs:25-51 ------------------ */
+int cvx_create(const cvx_config* config, cvx_ctx** out_ctx);
+int cvx_destroy(cvx_ctx* ctx);
+/* Error text of the last failing call on this context (or of cvx_create when ctx == NULL). */
+const char* cvx_last_error(const cvx_ctx* ctx);
+
+/* Optional: run on a caller-owned CUDA stream (cudaStream_t) instead of the context's own. */
+int cvx_set_stream(cvx_ctx* ctx, void* cuda_stream);
+
+/* ---- world hand-off: World / WorldAllocator, Assets/Code/World.cs:8-43,261-313 ------------
+ * blob = WorldAllocator.GetStartPointer()/GetByteLength(): column_count 12-byte RLEColumn
+ * headers followed by 4-byte RLEElement / ColorARGB32 cells. The host keeps its blob; the
+ * library copies it to the device (and builds its own device-side header layout). */
+int cvx_world_upload(cvx_ctx* ctx, int32_t lod, int32_t dim_x, int32_t dim_y, int32_t dim_z,
+                     const void* blob, int64_t bytes, int32_t column_count);
+int cvx_world_free(cvx_ctx* ctx);
+
+/* ---- RenderManager.SetResolution, RenderManager.cs:94-109 --------------------------------
+ * (re)allocates the top/down raybuffer H x (W+2H), the left/right raybuffer W x (2W+H)
+ * (RenderManager.cs:35-36) and the W x H framebuffer. */
+int cvx_set_resolution(cvx_ctx* ctx, int32_t width, int32_t height);
+
+/* ---- RenderManager.DrawSegments + ApplyPartials + BlitSegments ----------------------------
+ * cvx_draw runs Phase 1 for every ray of the four segments and Phase 2 for the whole screen,
+ * asynchronously on the context's stream. cvx_draw_rays runs Phase 1 only for the flat ray
+ * indices [ray_begin, ray_end) in RaySetupJob order (DrawSegmentRayJob.cs:12-40) and Phase 2
+ * only for screen rows [row_begin, row_end): the multi-GPU building blocks. */
+int cvx_draw(cvx_ctx* ctx, const cvx_frame_setup* setup);
+int cvx_draw_rays(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t ray_begin, int32_t ray_end);
+int cvx_blit_rows(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t row_begin, int32_t row_end);
+/* Multi-GPU Phase 2: write only the screen pixels whose source ray lies in [ray_begin, ray_end) into
+ * device_frame (a W*H*4 device buffer, possibly a peer GPU's mapped framebuffer; NULL = own frame).
+ * Ranks with disjoint ray ranges write disjoint pixels, so the gather is the store itself. */
+int cvx_blit_owned(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t ray_begin, int32_t ray_end, void* device_frame);
+/* Batched views over one world: n frames back to back, frame i
+ * read back (if dst_frames != NULL) to dst_frames + i*W*H*4. */
+int cvx_draw_batch(cvx_ctx* ctx, const cvx_frame_setup* setups, int32_t n_views, void* dst_frames);
+int cvx_sync(cvx_ctx* ctx);
+
+/* ---- outputs --------------------------------------------------------------------------------
+ * Pixels are ColorARGB32 (bytes a,r,g,b; Assets/Code/Utils/Color24.cs:5-11). The frame is
+ * W*H pixels, row 0 = bottom of the screen (Unity screen space, as RenderManager uses it).
+ * Raybuffers are flat: row r (one ray) at r*row_len pixels — the RenderTexture contents after
+ * RayBuffer.ApplyPartials (RayBuffer.cs:79-89). which: 0 = top/down, 1 = left/right. */
+int cvx_read_frame(cvx_ctx* ctx, void* dst_argb, int64_t bytes);
+int cvx_read_raybuffer(cvx_ctx* ctx, int32_t which, void* dst_argb, int64_t bytes);
+int cvx_get_counters(cvx_ctx* ctx, cvx_counters* out, int32_t reset);
+/* Debug: fill both raybuffers with one colour (RenderManager.ClearRayBuffer, RenderManager.cs:58-92 uses magenta). */
+int cvx_clear_raybuffers(cvx_ctx* ctx, uint32_t argb);
+/* Page-locked host memory for asynchronous frame readback (cvx_draw_batch, cvx_read_frame). */
+int cvx_alloc_pinned(int64_t bytes, void** out);
+int cvx_free_pinned(void* p);
+/* Device pointers for interop (display, NCCL gather): valid until the next cvx_set_resolution. */
+int cvx_device_frame(cvx_ctx* ctx, void** out_device_ptr, int64_t* out_bytes);
+int cvx_device_raybuffer(cvx_ctx* ctx, int32_t which, void** out_device_ptr, int64_t* out_bytes);
+/* Render into a caller-owned device framebuffer (W*H*4 bytes) instead of the internal one;
+ * NULL restores the internal buffer. */
+int cvx_set_external_frame(cvx_ctx* ctx, void* device_ptr);
+/* Timing of the last cvx_draw on the device, in milliseconds (CUDA events on the stream). */
+int cvx_last_draw_ms(cvx_ctx* ctx, float* out_phase1_ms, float* out_phase2_ms);
+/* Number of kernel launches issued by this context since creation. */
+int64_t cvx_launch_count(const cvx_ctx* ctx);
+
+/* Debug: dump the per-ray state after RaySetupJob/DDASetupJob/TraceToFirstColumnJob
+ * (DrawSegmentRayJob.cs:12-144) for every flat ray index; 16 x 4 bytes per ray, see cvx_ray_state. */
+typedef struct cvx_ray_state {
+    int32_t segment;
+    int32_t plane_ray_index;
+    int32_t status;          /* 0 = continues into RenderJob, 1 = skybox-filled in TraceToFirstColumn */
+    int32_t lod;
+    int32_t position[2];
+    int32_t step[2];
+    float start[2];
+    float dir[2];
+    float t_delta[2];
+    float t_max[2];
+    float intersection_distances[2];
+} cvx_ray_state;
+int cvx_debug_ray_setup(cvx_ctx* ctx, const cvx_frame_setup* setup, cvx_ray_state* out, int32_t max_rays);
+
+/* =============================================================================================
+ * Host-side helpers (pure CPU, no device): C++ restatement of the managed code around the path,
+ * for hosts that have no UnityEngine (tests, bench, headless servers). A Unity host keeps using
+ * RenderManager's own code for these and only calls the device entry points above.
+ * ============================================================================================= */
+
+/* UnityEngine.Camera + Transform state that RenderManager.DrawWorld reads. */
+typedef struct cvx_pose {
+    float position[3];
+    float rotation[4];     /* quaternion x,y,z,w */
+    float fov_y_degrees;   /* SampleScene.unity:178 = 85 */
+    float near_clip;       /* SampleScene.unity:176 = 0.05 */
+    float far_clip;        /* UnityManager.SetupLods: 2 * world max dimension */
+    int32_t pixel_width;
+    int32_t pixel_height;
+} cvx_pose;
+
+/* Quaternion.Euler(x,y,z) (Z-X-Y order), degrees. */
+void cvx_host_quat_euler(float x_deg, float y_deg, float z_deg, float out_quat[4]);
+/* UnityManager.LimitRotationHorizon, UnityManager.cs:193-201. */
+void cvx_host_limit_rotation_horizon(cvx_pose* pose);
+/* UnityManager.SetupLods, UnityManager.cs:417-458 (window size == render resolution). */
+void cvx_host_setup_lods(int32_t world_max_dimension, int32_t res_x, int32_t res_y,
+                         float fov_y_degrees, float lod_error, float out_lod_distances[CVX_LOD_LEVELS]);
+/* RenderManager.DrawWorld up to the DrawSegments call: vanishing point (RenderManager.cs:374-394),
+ * GetGenericSegmentParameters x4 (:402-501), CameraData ctor (CameraData.cs:18-36). */
+int cvx_host_frame_setup(const cvx_pose* pose, const float lod_distances[CVX_LOD_LEVELS],
+                         int32_t world_dim_y, cvx_frame_setup* out);
+/* BenchmarkPath.anim sampled at clip time t in [0, 1.15] (UnityManager.cs:86-87): position is
+ * the normalised curve value times the world dimensions; rotation from the Euler curves. */
+void cvx_host_benchmark_pose(float clip_time, const int32_t world_dims[3], cvx_pose* inout_pose);
+float cvx_host_benchmark_length(void);
+
+/* ---- world production (host, offline): ObjModel/SimpleMesh/VoxelizerHelper/WorldBuilder/
+ * World.DownSample restated (Assets/Code/Utils/ObjModel.cs, SimpleMesh.cs:64-106,
+ * VoxelizerHelper.cs:28-132, WordBuilder.cs:39-268, World.cs:45-127). */
+typedef struct cvx_world_builder cvx_world_builder;
+/* vertices: n_vertices x {x,y,z} float + n_vertices x {r,g,b,a} bytes (Color32); triangles are
+ * consecutive vertex triples (the .obj importer emits non-indexed meshes). flips: 1 = flip axis. */
+int cvx_builder_from_mesh(const float* positions, const uint8_t* colors32, int32_t n_vertices,
+                          int32_t max_dimension, const int32_t flips[3], int32_t n_threads,
+                          cvx_world_builder** out);
+/* Parse a text .obj (v with optional rgb, f with v, v/vt, v/vt/vn or v//vn) into the arrays above. */
+int cvx_obj_parse(const char* path, int32_t swap_yz, float** out_positions, uint8_t** out_colors32,
+                  int32_t* out_n_vertices);
+void cvx_host_free(void* p);
+/* Synthetic worlds of BASELINE.json configs 2-5; kind 0 = fBm heightmap shell,
+ * kind 1 = structured boxes/pipes/slabs. */
+int cvx_builder_synthetic(int32_t kind, int32_t dim_x, int32_t dim_y, int32_t dim_z, uint32_t seed,
+                          int32_t n_threads, cvx_world_builder** out);
+int cvx_builder_dims(const cvx_world_builder* b, int32_t out_dims[3]);
+/* Build LOD `lod` (0 = ToLOD0World, j>0 = World.DownSample(j) of LOD 0); the blob stays owned by
+ * the builder. voxel_count = the count the reference logs per LOD (UnityManager.cs:326-331). */
+int cvx_builder_lod(cvx_world_builder* b, int32_t lod, const void** out_blob, int64_t* out_bytes,
+                    int32_t* out_column_count, int64_t* out_voxel_count);
+void cvx_builder_free(cvx_world_builder* b);
+
+/* ---- .world files, Assets/Code/WorldSaveFile.cs:8-103 ---------------------------------------- */
+int cvx_world_file_write(const char* path, const int32_t dims[3], int32_t world_count,
+                         const void* const* blobs, const int64_t* blob_bytes);
+/* Reads header + table; blobs are malloc'ed (free each with cvx_host_free). */
+int cvx_world_file_read(const char* path, int32_t out_dims[3], int32_t* out_world_count,
+                        void** out_blobs /* [CVX_LOD_LEVELS] */, int64_t* out_blob_bytes /* [CVX_LOD_LEVELS] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPUVOX_B200_H */
