@@ -12,6 +12,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/cpuvox_b200.h"
 #include "device_types.h"
@@ -40,6 +41,9 @@ struct cvx_ctx {
     cudaEvent_t evFrameDone[2] = {nullptr, nullptr}, evCopyDone[2] = {nullptr, nullptr};
     bool timed = false;
     int64_t launches = 0;
+    std::vector<cudaEvent_t> profEvents; // 3 per profiled view: start, mid, end
+    int profCapacity = 0, profCount = 0;
+    int groupSize = 0;                  // lanes per ray in phase 1: 0 = auto, 8, 16, 32
     std::string error;
 };
 
@@ -205,6 +209,7 @@ int cvx_destroy(cvx_ctx* ctx) {
     if (ctx->copyStream) cudaStreamSynchronize(ctx->copyStream);
     free_resolution(ctx);
     free_world(ctx);
+    for (cudaEvent_t e : ctx->profEvents) cudaEventDestroy(e);
     cudaFree(ctx->counters);
     if (ctx->evStart) cudaEventDestroy(ctx->evStart);
     if (ctx->evMid) cudaEventDestroy(ctx->evMid);
@@ -329,7 +334,7 @@ int cvx_draw_rays(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t ray_begin,
     f.ray_begin = ray_begin; f.ray_end = ray_end;
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaEventRecord(ctx->evStart, ctx->stream));
-    CU(ctx, cvxd_launch_phase1(ctx->world, f, ctx->stream));
+    CU(ctx, cvxd_launch_phase1(ctx->world, f, ctx->groupSize, ctx->stream));
     if (ray_end > ray_begin) ctx->launches++;
     CU(ctx, cudaEventRecord(ctx->evMid, ctx->stream));
     CU(ctx, cudaEventRecord(ctx->evEnd, ctx->stream));
@@ -376,13 +381,18 @@ static int draw_into(cvx_ctx* ctx, const cvx_frame_setup* setup, uint32_t* targe
     if (r) return r;
     cvxd_blit b;
     make_blit(ctx, f, target, b);
+    const bool prof = ctx->profCount < ctx->profCapacity;
+    cudaEvent_t* pe = prof ? &ctx->profEvents[3 * (size_t)ctx->profCount] : nullptr;
     if (timed) CU(ctx, cudaEventRecord(ctx->evStart, ctx->stream));
-    CU(ctx, cvxd_launch_phase1(ctx->world, f, ctx->stream));
+    if (prof) CU(ctx, cudaEventRecord(pe[0], ctx->stream));
+    CU(ctx, cvxd_launch_phase1(ctx->world, f, ctx->groupSize, ctx->stream));
     if (f.total_rays > 0) ctx->launches++;
     if (timed) CU(ctx, cudaEventRecord(ctx->evMid, ctx->stream));
+    if (prof) CU(ctx, cudaEventRecord(pe[1], ctx->stream));
     CU(ctx, cvxd_launch_phase2(b, ctx->stream));
     ctx->launches++;
     if (timed) { CU(ctx, cudaEventRecord(ctx->evEnd, ctx->stream)); ctx->timed = true; }
+    if (prof) { CU(ctx, cudaEventRecord(pe[2], ctx->stream)); ctx->profCount++; }
     return CVX_OK;
 }
 
@@ -507,6 +517,59 @@ int cvx_last_draw_ms(cvx_ctx* ctx, float* out_phase1_ms, float* out_phase2_ms) {
 }
 
 int64_t cvx_launch_count(const cvx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int cvx_set_option(cvx_ctx* ctx, int32_t option, int32_t value) {
+    if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
+    switch (option) {
+    case CVX_OPT_GROUP_SIZE:
+        if (value != 0 && value != 8 && value != 16 && value != 32) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "group size %d: expected 0, 8, 16 or 32", value);
+        ctx->groupSize = value;
+        return CVX_OK;
+    case CVX_OPT_COUNTERS:
+        ctx->flags = value ? (ctx->flags | CVX_FLAG_COUNTERS) : (ctx->flags & ~CVX_FLAG_COUNTERS);
+        return CVX_OK;
+    default:
+        return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "unknown option %d", option);
+    }
+}
+
+static void free_profile(cvx_ctx* ctx) {
+    for (cudaEvent_t e : ctx->profEvents) cudaEventDestroy(e);
+    ctx->profEvents.clear();
+    ctx->profCapacity = ctx->profCount = 0;
+}
+
+int cvx_profile_begin(cvx_ctx* ctx, int32_t max_draws) {
+    if (!ctx || max_draws < 1 || max_draws > (1 << 20)) return CVX_ERR_INVALID_ARGUMENT;
+    CU(ctx, cudaSetDevice(ctx->device));
+    free_profile(ctx);
+    ctx->profEvents.reserve(3 * (size_t)max_draws);
+    for (int i = 0; i < 3 * max_draws; i++) {
+        cudaEvent_t e;
+        CU(ctx, cudaEventCreate(&e));
+        ctx->profEvents.push_back(e);
+    }
+    ctx->profCapacity = max_draws;
+    return CVX_OK;
+}
+
+int cvx_profile_end(cvx_ctx* ctx, double* out_phase1_ms, double* out_phase2_ms, int32_t* out_draws) {
+    if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    double p1 = 0.0, p2 = 0.0;
+    for (int i = 0; i < ctx->profCount; i++) {
+        float a = 0.0f, b = 0.0f;
+        CU(ctx, cudaEventElapsedTime(&a, ctx->profEvents[3 * (size_t)i], ctx->profEvents[3 * (size_t)i + 1]));
+        CU(ctx, cudaEventElapsedTime(&b, ctx->profEvents[3 * (size_t)i + 1], ctx->profEvents[3 * (size_t)i + 2]));
+        p1 += a; p2 += b;
+    }
+    if (out_phase1_ms) *out_phase1_ms = p1;
+    if (out_phase2_ms) *out_phase2_ms = p2;
+    if (out_draws) *out_draws = ctx->profCount;
+    free_profile(ctx);
+    return CVX_OK;
+}
 
 int cvx_debug_ray_setup(cvx_ctx* ctx, const cvx_frame_setup* setup, cvx_ray_state* out, int32_t max_rays) {
     int r = check_ready(ctx, setup);

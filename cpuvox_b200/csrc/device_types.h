@@ -8,8 +8,7 @@
 
 #define CVXD_LODS 6
 #define CVXD_MAX_AXIS 8192          /* longest raybuffer row (max(W,H)) the seen-mask in shared memory supports */
-#define CVXD_SEEN_WORDS (CVXD_MAX_AXIS / 32)
-#define CVXD_WARPS_PER_CTA 4
+#define CVXD_THREADS_PER_CTA 128
 
 /* Device copy of one World LOD (Assets/Code/World.cs:8-43,161-188). Headers are transcoded at upload from the
  * reference's 12-byte RLEColumn into one 16-byte aligned uint4 per column so a lane fetches a column header with
@@ -82,7 +81,7 @@ struct cvxd_ray_state { /* mirrors cvx_ray_state */
 };
 
 #ifdef __CUDACC__
-cudaError_t cvxd_launch_phase1(const cvxd_world& world, const cvxd_frame& frame, cudaStream_t stream);
+cudaError_t cvxd_launch_phase1(const cvxd_world& world, const cvxd_frame& frame, int group_size, cudaStream_t stream);
 cudaError_t cvxd_launch_phase2(const cvxd_blit& blit, cudaStream_t stream);
 cudaError_t cvxd_launch_ray_setup(const cvxd_world& world, const cvxd_frame& frame, cvxd_ray_state* out, int n, cudaStream_t stream);
 cudaError_t cvxd_launch_transcode_headers(const uint8_t* blob_headers12, uint4* out, const uint32_t* elements, int64_t n_columns, cudaStream_t stream);

@@ -244,6 +244,17 @@ __device__ __forceinline__ int scan_down(const uint32_t* seen, int start, int li
     }
     return limit - 1 < start ? limit - 1 : start;
 }
+// bits [a & 31 .. 31] of the word holding a, and bits [0 .. b & 31] of the word holding b
+__device__ __forceinline__ uint32_t mask_from(int a) { return FULL_MASK << (a & 31); }
+__device__ __forceinline__ uint32_t mask_to(int b) { return FULL_MASK >> (31 - (b & 31)); }
+// any clear bit in [a, b] (a <= b, both inside the row)
+__device__ __forceinline__ bool any_unseen(const uint32_t* seen, int a, int b) {
+    const int wa = a >> 5, wb = b >> 5;
+    if (wa == wb) return (~seen[wa] & mask_from(a) & mask_to(b)) != 0u;
+    if (~seen[wa] & mask_from(a)) return true;
+    for (int w = wa + 1; w < wb; w++) if (~seen[w]) return true;
+    return (~seen[wb] & mask_to(b)) != 0u;
+}
 
 struct RowState {
     uint32_t* seen;         // shared-memory bitmask of this row
@@ -253,7 +264,17 @@ struct RowState {
     float fb_min, fb_max;   // frustumBoundsMin/Max
 };
 
-// ReducePixelHorizon :660-697 (uniform across the warp)
+// A span [bMin, bMax] changes anything (pixels, horizon, frustum) only if it holds a still-unwritten pixel of the
+// writable range: nextFreePixelMin/Max are themselves unwritten pixels (the scans of :407-415,678-692 stop on one),
+// so a span that reaches an end of the range (the only way ReducePixelHorizon :660-697 moves the horizon) always
+// contains one. Everything else passes the overlap test of :505/:581, writes nothing and leaves all state untouched.
+__device__ __forceinline__ bool span_would_write(const RowState& rw, int bMin, int bMax) {
+    if (!(bMax >= rw.nf_min && bMin <= rw.nf_max)) return false;
+    const int a = bMin > rw.nf_min ? bMin : rw.nf_min, b = bMax < rw.nf_max ? bMax : rw.nf_max;
+    return a <= b && any_unseen(rw.seen, a, b);
+}
+
+// ReducePixelHorizon :660-697 (uniform across the group)
 __device__ __forceinline__ void reduce_pixel_horizon(RowState& rw, int& bMin, int& bMax) {
     if (bMin <= rw.nf_min) {
         bMin = rw.nf_min;
@@ -271,31 +292,34 @@ __device__ __forceinline__ void reduce_pixel_horizon(RowState& rw, int& bMin, in
     }
 }
 
-// WriteSkybox :699-708 — every still-unwritten pixel of the row's range, 32 pixels per step
-__device__ __forceinline__ int sky_fill(const RowState& rw, int lane) {
-    int written = 0;
-    for (int w = rw.orig_min >> 5; w <= rw.orig_max >> 5; w++) {
-        int y = (w << 5) + lane;
-        bool put = y >= rw.orig_min && y <= rw.orig_max && !((rw.seen[w] >> lane) & 1u);
-        if (put) rw.row[y] = SKYBOX_ARGB;
-        written += __popc(__ballot_sync(FULL_MASK, put));
-    }
-    return written;
-}
-// WriteSkyboxFull :710-716
-__device__ __forceinline__ int sky_fill_all(uint32_t* row, int mn, int mx, int lane) {
-    for (int y = mn + lane; y <= mx; y += 32) row[y] = SKYBOX_ARGB;
-    return mx >= mn ? mx - mn + 1 : 0;
-}
-
 struct Acc { unsigned long long dda_steps, columns_nonempty, runs_visited, px_voxel, px_sky; };
 
-__global__ void __launch_bounds__(CVXD_WARPS_PER_CTA * 32)
+// Load whose result is never used: pulls the line into L1/L2 ahead of the dependent loads of the column body.
+__device__ __forceinline__ void touch(const uint32_t* p) {
+    uint32_t sink;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(sink) : "l"(p));
+}
+
+/*
+ * phase1_kernel<G, COUNTERS>: one GROUP of G lanes (8, 16 or 32) per raybuffer row, 32/G rows per warp.
+ * Neighbouring rows (adjacent rays of one segment) share a warp: they walk nearly the same columns, so the groups of
+ * a warp stay mostly convergent while the number of rays in flight per SM grows by 32/G.
+ */
+template <int G, bool COUNTERS>
+__global__ void __launch_bounds__(CVXD_THREADS_PER_CTA)
 phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ cvxd_frame f) {
-    __shared__ uint32_t seen_all[CVXD_WARPS_PER_CTA][CVXD_SEEN_WORDS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int flat = f.ray_begin + blockIdx.x * CVXD_WARPS_PER_CTA + warp;
+    extern __shared__ uint32_t seen_all[];
+    constexpr int GROUPS_PER_CTA = CVXD_THREADS_PER_CTA / G;
+    constexpr uint32_t GBITS = G == 32 ? FULL_MASK : ((1u << (G & 31)) - 1u);
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1);          // lane inside the group
+    const int gshift = lane & ~(G - 1);     // first lane of the group inside the warp
+    const uint32_t gmask = GBITS << gshift;
+    const int group = threadIdx.x / G;
+    const int flat = f.ray_begin + blockIdx.x * GROUPS_PER_CTA + group;
     if (flat >= f.ray_end) return;
+#define GBALLOT(p) ((__ballot_sync(gmask, (p)) >> gshift) & GBITS)
+#define GSHFL(v, src) __shfl_sync(gmask, (v), (src), G)
 
     RaySetup rs;
     setup_ray(world, f, flat, rs);
@@ -303,20 +327,23 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
     const cvxd_segment& sg = f.seg[rs.segment];
     const int rowLen = sg.buffer == 0 ? f.height : f.width;
     uint32_t* row = (sg.buffer == 0 ? f.td : f.lr) + (int64_t)(rs.plane_index + sg.ray_index_offset) * rowLen;
+    const int seenWords = ((f.width > f.height ? f.width : f.height) + 31) >> 5;
 
-    Acc acc = {(unsigned long long)rs.lod_steps, 0, 0, 0, 0};
+    Acc acc = {0, 0, 0, 0, 0}; // per lane; summed with atomics at the end (COUNTERS only)
+    if (COUNTERS && gl == 0) acc.dda_steps = (unsigned long long)rs.lod_steps;
     RowState rw;
-    rw.seen = seen_all[warp];
+    rw.seen = seen_all + group * seenWords;
     rw.row = row;
     rw.orig_min = sg.pix_min; rw.orig_max = sg.pix_max;
     rw.nf_min = rw.orig_min; rw.nf_max = rw.orig_max;
     rw.fb_min = rw.nf_min - 0.501f; rw.fb_max = rw.nf_max + 0.501f;
 
-    if (rs.status == 1) {
-        acc.px_sky += sky_fill_all(row, rw.orig_min, rw.orig_max, lane);
+    if (rs.status == 1) { // WriteSkyboxFull :710-716
+        for (int y = rw.orig_min + gl; y <= rw.orig_max; y += G) row[y] = SKYBOX_ARGB;
+        if (COUNTERS && gl == 0 && rw.orig_max >= rw.orig_min) acc.px_sky += rw.orig_max - rw.orig_min + 1;
     } else {
-        for (int w = lane; w < ((rowLen + 31) >> 5); w += 32) rw.seen[w] = 0u; // stackalloc, zero-initialised (:208)
-        __syncwarp();
+        for (int w = gl; w < ((rowLen + 31) >> 5); w += G) rw.seen[w] = 0u; // stackalloc, zero-initialised (:208)
+        __syncwarp(gmask);
 
         Dda ray = rs.dda;
         int lod = rs.lod;
@@ -347,17 +374,17 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
         bool terminated = false; // ray ended inside the loop: skybox the rest and stop
         bool reachedEnd = false; // far clip or world exit
         while (!terminated && !reachedEnd) {
-            // ---- look ahead: up to 32 cells of the DDA, lane i keeps cell i ------------------------------------
+            // ---- look ahead: up to G cells of the DDA, lane i of the group keeps cell i -------------------------
             int n = 0, endKind = 0; // 1 = next cell is outside the world, 2 = far clip crossed after the last cell
             int myLod = 0, myIdx = 0; float myDl = 0.0f, myDn = 0.0f;
-            for (int i = 0; i < 32; i++) {
+            for (int i = 0; i < G; i++) {
                 if (ray.dl >= lodMax) { // :237-243
                     dda_next_lod(ray, voxelScale);
                     lod++; voxelScale *= 2;
                     lodMax = f.lod_dist[lod];
                 }
                 if (((ray.px & maskX) != ray.px) || ((ray.pz & maskZ) != ray.pz)) { endKind = 1; break; } // World.cs:135-138
-                if (lane == i) {
+                if (gl == i) {
                     myLod = lod; myDl = ray.dl; myDn = ray.dn;
                     myIdx = (ray.px >> lod) * world.lods[lod].mul_x + (ray.pz >> lod); // GetIndexKnownInBounds World.cs:145-149
                 }
@@ -365,34 +392,48 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                 if (dda_step(ray, farClip)) { endKind = 2; break; }
             }
             uint4 hdr = make_uint4(0, 0, 0, 0);
-            if (lane < n) hdr = __ldg(world.lods[myLod].headers + myIdx);
-            uint32_t nonEmpty = __ballot_sync(FULL_MASK, (hdr.y & 0xffffu) != 0u);
+            if (gl < n) hdr = __ldg(world.lods[myLod].headers + myIdx);
+            const bool myNonEmpty = (hdr.y & 0xffffu) != 0u;
+            // start fetching the run list of every non-empty column of the batch now; the column bodies below find it cached
+            if (myNonEmpty) touch(world.lods[myLod].elements + hdr.x + (ITER > 0 ? 1u : (hdr.y & 0xffffu)));
+            const float myWorldMin = (float)(hdr.y >> 16), myWorldMax = (float)(hdr.z & 0xffffu);
+            uint32_t remaining = GBALLOT(myNonEmpty);
             int cellsDone = n + (endKind == 1 ? 1 : 0); // the out-of-world probe counts as a step
 
-            while (nonEmpty) {
-                const int c = __ffs(nonEmpty) - 1;
-                nonEmpty &= nonEmpty - 1;
-                const float distLast = __shfl_sync(FULL_MASK, myDl, c);
-                const float distNext = __shfl_sync(FULL_MASK, myDn, c);
-                const int cLod = __shfl_sync(FULL_MASK, myLod, c);
-                const uint32_t hOff = __shfl_sync(FULL_MASK, hdr.x, c);
-                const uint32_t hY = __shfl_sync(FULL_MASK, hdr.y, c);
-                const uint32_t hZ = __shfl_sync(FULL_MASK, hdr.z, c);
-                const int runCount = (int)(hY & 0xffffu);
-                const float colWorldMin = (float)(hY >> 16), colWorldMax = (float)(hZ & 0xffffu);
-                const int cScale = 1 << cLod;
-                acc.columns_nonempty++;
-
+            while (remaining) {
+                // ---- next column that is not culled by the narrowed frustum (:261-281), found for all columns at once ----
+                int c;
                 float worldBoundsMin = 0.0f, worldBoundsMax = worldMaxY;
-                if (frustumDirMaxWorld != EPS) { // :261-281
-                    float distTop = frustumDirMaxWorld > 0.0f ? distNext : distLast;
-                    float distBot = frustumDirMinWorld < 0.0f ? distNext : distLast;
-                    float newMax = camY + frustumDirMaxWorld * distTop;
-                    float newMin = camY + frustumDirMinWorld * distBot;
-                    if (newMin > worldBoundsMax || newMax < worldBoundsMin) { terminated = true; cellsDone = c + 1; break; }
-                    if (colWorldMin > newMax || colWorldMax < newMin) continue;
-                    worldBoundsMin = newMin; worldBoundsMax = newMax;
+                if (frustumDirMaxWorld != EPS) {
+                    const float distTop = frustumDirMaxWorld > 0.0f ? myDn : myDl;
+                    const float distBot = frustumDirMinWorld < 0.0f ? myDn : myDl;
+                    const float newMax = camY + frustumDirMaxWorld * distTop;
+                    const float newMin = camY + frustumDirMinWorld * distBot;
+                    const bool outOfWorld = newMin > worldMaxY || newMax < 0.0f;      // frustum left the world: ray ends
+                    const bool culled = myWorldMin > newMax || myWorldMax < newMin;   // column outside the writable world bounds
+                    const uint32_t cand = GBALLOT(myNonEmpty && (outOfWorld || !culled)) & remaining;
+                    if (!cand) {
+                        if (COUNTERS && gl == 0) acc.columns_nonempty += __popc(remaining);
+                        remaining = 0u;
+                        break;
+                    }
+                    c = __ffs(cand) - 1;
+                    const uint32_t upto = remaining & ((2u << c) - 1u);
+                    if (COUNTERS && gl == 0) acc.columns_nonempty += __popc(upto);
+                    remaining &= ~upto;
+                    if (GSHFL((int)outOfWorld, c)) { terminated = true; cellsDone = c + 1; break; }
+                    worldBoundsMin = GSHFL(newMin, c); worldBoundsMax = GSHFL(newMax, c);
+                } else {
+                    c = __ffs(remaining) - 1;
+                    remaining &= remaining - 1;
+                    if (COUNTERS && gl == 0) acc.columns_nonempty++;
                 }
+                const float distLast = GSHFL(myDl, c);
+                const float distNext = GSHFL(myDn, c);
+                const int cLod = GSHFL(myLod, c);
+                const uint32_t hOff = GSHFL(hdr.x, c);
+                const int runCount = (int)(GSHFL(hdr.y, c) & 0xffffu);
+                const int cScale = 1 << cLod;
 
                 // :289-293
                 const F3 minLast = F3{planeBottom.x + planeDir.x * distLast, planeBottom.y + planeDir.y * distLast, planeBottom.z + planeDir.z * distLast};
@@ -401,9 +442,21 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                 const F3 maxNext = F3{planeTop.x + planeDir.x * distNext, planeTop.y + planeDir.y * distNext, planeTop.z + planeDir.z * distNext};
 
                 if (distLast > 2.0f && frustumDirMaxWorld == EPS) { // re-narrow the frustum :295-422
-                    float lastMinL, lastMaxL, nextMinL, nextMaxL;
-                    bool clippedLast = world_bounds_clipping(minLast, maxLast, rw.fb_min, rw.fb_max, lastMinL, lastMaxL);
-                    bool clippedNext = world_bounds_clipping(minNext, maxNext, rw.fb_min, rw.fb_max, nextMinL, nextMaxL);
+                    // The four clip parameters (last/next line x min/max end) and their projections are independent:
+                    // lane L&3 of the group computes one of them (same operations as CameraData.cs:50-121), then they are shared.
+                    const int L = gl & 3;
+                    const F3 pMin = (L & 2) ? minNext : minLast, pMax = (L & 2) ? maxNext : maxLast;
+                    const bool A = pMin.x > pMin.z * rw.fb_max, B = pMax.x > pMax.z * rw.fb_max;
+                    const bool C = pMin.x < pMin.z * rw.fb_min, D = pMax.x < pMax.z * rw.fb_min;
+                    const bool clipped = (A && B) || (!A && !B && C && D);
+                    float myLerp;
+                    if (L & 1) myLerp = B ? clip_max(pMin, pMax, rw.fb_max) : (D ? clip_max(pMin, pMax, rw.fb_min) : 1.0f);
+                    else       myLerp = A ? clip_min(pMin, pMax, rw.fb_max) : (C ? clip_min(pMin, pMax, rw.fb_min) : 0.0f);
+                    const F3 pc = lerp3(pMin, pMax, myLerp);
+                    const float myProj = pc.x / pc.z;
+                    const float lastMinL = GSHFL(myLerp, 0), lastMaxL = GSHFL(myLerp, 1), nextMinL = GSHFL(myLerp, 2), nextMaxL = GSHFL(myLerp, 3);
+                    float mnL = GSHFL(myProj, 0), mxL = GSHFL(myProj, 1), mnN = GSHFL(myProj, 2), mxN = GSHFL(myProj, 3);
+                    const bool clippedLast = GSHFL((int)clipped, 0) != 0, clippedNext = GSHFL((int)clipped, 2) != 0;
                     float clippedMin, clippedMax;
                     if (clippedLast) {
                         if (clippedNext) { terminated = true; cellsDone = c + 1; break; }
@@ -411,16 +464,14 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                         worldBoundsMax = lerpf(0.0f, worldMaxY, nextMaxL);
                         frustumDirMaxWorld = (worldBoundsMax - camY) / distNext;
                         frustumDirMinWorld = (worldBoundsMin - camY) / distNext;
-                        F3 a = lerp3(minNext, maxNext, nextMinL), b = lerp3(minNext, maxNext, nextMaxL);
-                        clippedMin = a.x / a.z; clippedMax = b.x / b.z;
+                        clippedMin = mnN; clippedMax = mxN;
                         if (clippedMax < clippedMin) { float t = clippedMin; clippedMin = clippedMax; clippedMax = t; }
                     } else if (clippedNext) {
                         worldBoundsMin = lerpf(0.0f, worldMaxY, lastMinL);
                         worldBoundsMax = lerpf(0.0f, worldMaxY, lastMaxL);
-                        F3 a = lerp3(minLast, maxLast, lastMinL), b = lerp3(minLast, maxLast, lastMaxL);
                         frustumDirMaxWorld = (worldBoundsMax - camY) / distLast;
                         frustumDirMinWorld = (worldBoundsMin - camY) / distLast;
-                        clippedMin = a.x / a.z; clippedMax = b.x / b.z;
+                        clippedMin = mnL; clippedMax = mxL;
                         if (clippedMax < clippedMin) { float t = clippedMin; clippedMin = clippedMax; clippedMax = t; }
                     } else {
                         if (lastMinL < nextMinL) {
@@ -437,9 +488,6 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                             worldBoundsMax = lerpf(0.0f, worldMaxY, nextMaxL);
                             frustumDirMaxWorld = (worldBoundsMax - camY) / distNext;
                         }
-                        F3 aA = lerp3(minLast, maxLast, lastMinL), bA = lerp3(minLast, maxLast, lastMaxL);
-                        F3 aB = lerp3(minNext, maxNext, nextMinL), bB = lerp3(minNext, maxNext, nextMaxL);
-                        float mnN = aB.x / aB.z, mnL = aA.x / aA.z, mxN = bB.x / bB.z, mxL = bA.x / bA.z;
                         if (mxN < mnN) { float t = mxN; mxN = mnN; mnN = t; }
                         if (mxL < mnL) { float t = mxL; mxL = mnL; mnL = t; }
                         clippedMin = minf_(mnL, mnN);
@@ -447,46 +495,46 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                     }
                     worldBoundsMin = floorf(worldBoundsMin);
                     worldBoundsMax = ceilf(worldBoundsMax);
-                    int writableMin = f2i(floorf(clippedMin));
-                    int writableMax = f2i(ceilf(clippedMax));
+                    const int writableMin = f2i(floorf(clippedMin));
+                    const int writableMax = f2i(ceilf(clippedMax));
                     if (writableMax < rw.nf_min || writableMin > rw.nf_max) { terminated = true; cellsDone = c + 1; break; }
                     if (writableMin > rw.nf_min) rw.nf_min = scan_up(rw.seen, writableMin, rw.orig_max);
                     if (writableMax < rw.nf_max) rw.nf_max = scan_down(rw.seen, writableMax, rw.orig_min);
                     if (rw.nf_min > rw.nf_max) { terminated = true; cellsDone = c + 1; break; }
                 }
 
-                // ---- runs of this column, 32 per pass, in iteration order (:424-611) ---------------------------
+                // ---- runs of this column, G per pass, in iteration order (:424-611) ----------------------------
                 const uint32_t* colBase = world.lods[cLod].elements + hOff;   // ElementGuardStart World.cs:175-178
                 const uint32_t* colColors = colBase + runCount + 2;           // ColorPointer :185-188
                 int chunkStartY = ITER > 0 ? world.dim_y : 0;                 // running elementBounds, exact in int
                 bool colStop = false;
-                for (int k0 = 0; k0 < runCount && !colStop && !terminated; k0 += 32) {
-                    const int k = k0 + lane;
+                for (int k0 = 0; k0 < runCount && !colStop && !terminated; k0 += G) {
+                    const int k = k0 + gl;
                     const bool inCol = k < runCount;
                     uint32_t el = inCol ? __ldg(colBase + (ITER > 0 ? 1 + k : runCount - k)) : 0u;
                     const int ci = (int)(short)(el & 0xffffu), len = (int)(short)(el >> 16); // RLEElement World.cs:245-259
                     // an invalid element (Length == 0) ends the column (:445-447)
-                    const uint32_t invalidMask = __ballot_sync(FULL_MASK, inCol && len == 0) | (runCount - k0 >= 32 ? 0u : (FULL_MASK << (runCount - k0)));
-                    const int nValid = invalidMask ? __ffs(invalidMask) - 1 : 32;
-                    const bool valid = lane < nValid;
+                    const uint32_t invalidMask = GBALLOT(!inCol || len == 0);
+                    const int nValid = invalidMask ? __ffs(invalidMask) - 1 : G;
+                    const bool valid = gl < nValid;
                     int span = valid ? len * cScale : 0;
                     int incl = span;
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += v; }
-                    const int chunkTotal = __shfl_sync(FULL_MASK, incl, 31);
+                    for (int o = 1; o < G; o <<= 1) { int v = __shfl_up_sync(gmask, incl, o, G); if (gl >= o) incl += v; }
+                    const int chunkTotal = GSHFL(incl, G - 1);
                     float eMin, eMax; // elementBoundsMin/Max :449-455
                     if (ITER > 0) { eMax = (float)(chunkStartY - (incl - span)); eMin = (float)(chunkStartY - incl); }
                     else          { eMin = (float)(chunkStartY + (incl - span)); eMax = (float)(chunkStartY + incl); }
                     chunkStartY += ITER > 0 ? -chunkTotal : chunkTotal;
-                    if (nValid < 32 && (k0 + nValid) < runCount) colStop = true; // hit an invalid element inside the column
+                    if (nValid < G && (k0 + nValid) < runCount) colStop = true; // hit an invalid element inside the column
 
                     const bool solid = valid && ci >= 0; // !IsAir
                     const bool above = eMin > worldBoundsMax, below = eMax < worldBoundsMin;
                     const bool isBreak = solid && (ITER > 0 ? (!above && below) : above); // :461-475 (above is tested first)
-                    const uint32_t breakMask = __ballot_sync(FULL_MASK, isBreak);
+                    const uint32_t breakMask = GBALLOT(isBreak);
                     int nVisit = nValid;
                     if (breakMask) { nVisit = __ffs(breakMask); colStop = true; } // the breaking run itself was dereferenced
-                    bool active = solid && lane < nVisit && !above && !below;
+                    const bool active = solid && gl < nVisit && !above && !below;
 
                     // ---- per-lane span geometry; depends only on column constants ------------------------------
                     bool sideOk = false, capOk = false;
@@ -523,82 +571,98 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                         }
                     }
 
-                    // ---- commit spans in reference order --------------------------------------------------------
-                    uint32_t todo = __ballot_sync(FULL_MASK, active && (sideOk || capOk));
+                    // ---- commit, in reference order, only the spans that still hold an unwritten pixel ----------
+                    uint32_t pending = GBALLOT(sideOk || capOk);
                     int visitedHere = nVisit;
-                    while (todo) {
-                        const int j = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        if (__shfl_sync(FULL_MASK, (int)sideOk, j)) {
-                            int bMin = __shfl_sync(FULL_MASK, sMin, j), bMax = __shfl_sync(FULL_MASK, sMax, j);
-                            if (bMax >= rw.nf_min && bMin <= rw.nf_max) { // :505
-                                reduce_pixel_horizon(rw, bMin, bMax);
-                                const float jbfx = __shfl_sync(FULL_MASK, bfx, j), jbfy = __shfl_sync(FULL_MASK, bfy, j);
-                                const float jAx = __shfl_sync(FULL_MASK, uvAx, j), jAy = __shfl_sync(FULL_MASK, uvAy, j);
-                                const float jBx = __shfl_sync(FULL_MASK, uvBx, j), jBy = __shfl_sync(FULL_MASK, uvBy, j);
-                                const int jLen = __shfl_sync(FULL_MASK, len, j), jCi = __shfl_sync(FULL_MASK, ci, j);
-                                int wrote = 0;
-                                if (bMin <= bMax) {
-                                    for (int w = bMin >> 5; w <= bMax >> 5; w++) { // :519-533
-                                        const int y = (w << 5) + lane;
-                                        const uint32_t sw = rw.seen[w];
-                                        const bool put = y >= bMin && y <= bMax && !((sw >> lane) & 1u);
-                                        if (put) {
-                                            float l = unlerpf(jbfx, jbfy, (float)y);
-                                            float wx = lerpf(jAx, jBx, l), wy = lerpf(jAy, jBy, l);
-                                            float u = wy / wx;
-                                            int idx = max(0, min(jLen - 1, f2i(floorf(u)))) + jCi;
-                                            row[y] = __ldg(colColors + idx);
-                                        }
-                                        const uint32_t pm = __ballot_sync(FULL_MASK, put);
-                                        if (pm) { if (lane == 0) rw.seen[w] = sw | pm; wrote += __popc(pm); }
-                                    }
-                                    __syncwarp();
+                    while (pending) {
+                        const bool wSide = sideOk && span_would_write(rw, sMin, sMax);
+                        const bool wCap = capOk && span_would_write(rw, cMin, cMax);
+                        const uint32_t hot = GBALLOT(wSide || wCap) & pending;
+                        if (!hot) break;
+                        const int j = __ffs(hot) - 1;
+                        pending &= ~((2u << j) - 1u);
+                        if (GSHFL((int)wSide, j)) { // side of run j :505-540
+                            int bMin = GSHFL(sMin, j), bMax = GSHFL(sMax, j);
+                            reduce_pixel_horizon(rw, bMin, bMax);
+                            const float jbfx = GSHFL(bfx, j), jbfy = GSHFL(bfy, j);
+                            const float jAx = GSHFL(uvAx, j), jAy = GSHFL(uvAy, j);
+                            const float jBx = GSHFL(uvBx, j), jBy = GSHFL(uvBy, j);
+                            const int jLen = GSHFL(len, j), jCi = GSHFL(ci, j);
+                            for (int y = bMin + gl; y <= bMax; y += G) { // :519-533
+                                if (!((rw.seen[y >> 5] >> (y & 31)) & 1u)) {
+                                    float l = unlerpf(jbfx, jbfy, (float)y);
+                                    float wx = lerpf(jAx, jBx, l), wy = lerpf(jAy, jBy, l);
+                                    float u = wy / wx;
+                                    int idx = max(0, min(jLen - 1, f2i(floorf(u)))) + jCi;
+                                    row[y] = __ldg(colColors + idx);
                                 }
-                                if (wrote) { frustumDirMaxWorld = EPS; acc.px_voxel += wrote; }
-                                if (rw.nf_min > rw.nf_max) { terminated = true; visitedHere = j + 1; break; } // :535-539
                             }
+                            __syncwarp(gmask);
+                            for (int w = (bMin >> 5) + gl; w <= (bMax >> 5); w += G) {
+                                uint32_t m = FULL_MASK;
+                                if (w == (bMin >> 5)) m &= mask_from(bMin);
+                                if (w == (bMax >> 5)) m &= mask_to(bMax);
+                                const uint32_t old = rw.seen[w];
+                                if (COUNTERS) acc.px_voxel += __popc(~old & m);
+                                rw.seen[w] = old | m;
+                            }
+                            __syncwarp(gmask);
+                            frustumDirMaxWorld = EPS; // a pixel was written (:522)
+                            if (rw.nf_min > rw.nf_max) { terminated = true; visitedHere = j + 1; break; } // :535-539
                         }
-                        if (__shfl_sync(FULL_MASK, (int)capOk, j)) {
-                            int bMin = __shfl_sync(FULL_MASK, cMin, j), bMax = __shfl_sync(FULL_MASK, cMax, j);
-                            if (bMax >= rw.nf_min && bMin <= rw.nf_max) { // :581
-                                reduce_pixel_horizon(rw, bMin, bMax);
-                                const uint32_t color = __ldg(colColors + __shfl_sync(FULL_MASK, capIdx, j));
-                                int wrote = 0;
-                                if (bMin <= bMax) {
-                                    for (int w = bMin >> 5; w <= bMax >> 5; w++) { // :595-602
-                                        const int y = (w << 5) + lane;
-                                        const uint32_t sw = rw.seen[w];
-                                        const bool put = y >= bMin && y <= bMax && !((sw >> lane) & 1u);
-                                        if (put) row[y] = color;
-                                        const uint32_t pm = __ballot_sync(FULL_MASK, put);
-                                        if (pm) { if (lane == 0) rw.seen[w] = sw | pm; wrote += __popc(pm); }
-                                    }
-                                    __syncwarp();
-                                }
-                                if (wrote) { frustumDirMaxWorld = EPS; acc.px_voxel += wrote; }
-                                if (rw.nf_min > rw.nf_max) { terminated = true; visitedHere = j + 1; break; } // :604-608
+                        // cap of run j :581-609, re-tested against the state the side span left behind
+                        const bool wCapNow = capOk && span_would_write(rw, cMin, cMax);
+                        if (GSHFL((int)wCapNow, j)) {
+                            int bMin = GSHFL(cMin, j), bMax = GSHFL(cMax, j);
+                            reduce_pixel_horizon(rw, bMin, bMax);
+                            const uint32_t color = __ldg(colColors + GSHFL(capIdx, j));
+                            for (int y = bMin + gl; y <= bMax; y += G) // :595-602
+                                if (!((rw.seen[y >> 5] >> (y & 31)) & 1u)) row[y] = color;
+                            __syncwarp(gmask);
+                            for (int w = (bMin >> 5) + gl; w <= (bMax >> 5); w += G) {
+                                uint32_t m = FULL_MASK;
+                                if (w == (bMin >> 5)) m &= mask_from(bMin);
+                                if (w == (bMax >> 5)) m &= mask_to(bMax);
+                                const uint32_t old = rw.seen[w];
+                                if (COUNTERS) acc.px_voxel += __popc(~old & m);
+                                rw.seen[w] = old | m;
                             }
+                            __syncwarp(gmask);
+                            frustumDirMaxWorld = EPS; // :598
+                            if (rw.nf_min > rw.nf_max) { terminated = true; visitedHere = j + 1; break; } // :604-608
                         }
                     }
-                    acc.runs_visited += visitedHere;
+                    if (COUNTERS && gl == 0) acc.runs_visited += visitedHere;
                 }
                 if (terminated) { cellsDone = c + 1; break; }
             }
-            acc.dda_steps += cellsDone;
+            if (COUNTERS && gl == 0) acc.dda_steps += cellsDone;
             if (endKind != 0) reachedEnd = true;
         }
-        acc.px_sky += sky_fill(rw, lane); // :248,268,323,401,419,537,606,619 all end in WriteSkybox
+        // WriteSkybox :699-708 — :248,268,323,401,419,537,606,619 all end here
+        __syncwarp(gmask);
+        for (int y = rw.orig_min + gl; y <= rw.orig_max; y += G)
+            if (!((rw.seen[y >> 5] >> (y & 31)) & 1u)) row[y] = SKYBOX_ARGB;
+        if (COUNTERS) {
+            for (int w = (rw.orig_min >> 5) + gl; w <= (rw.orig_max >> 5); w += G) {
+                uint32_t m = FULL_MASK;
+                if (w == (rw.orig_min >> 5)) m &= mask_from(rw.orig_min);
+                if (w == (rw.orig_max >> 5)) m &= mask_to(rw.orig_max);
+                acc.px_sky += __popc(~rw.seen[w] & m);
+            }
+        }
     }
 
-    if (f.counters && lane == 0) {
-        atomicAdd(&f.counters->dda_steps, acc.dda_steps);
-        atomicAdd(&f.counters->columns_nonempty, acc.columns_nonempty);
-        atomicAdd(&f.counters->runs_visited, acc.runs_visited);
-        atomicAdd(&f.counters->px_voxel, acc.px_voxel);
-        atomicAdd(&f.counters->px_sky, acc.px_sky);
-        atomicAdd(&f.counters->rays, 1ull);
+    if (COUNTERS && f.counters) {
+        if (acc.dda_steps) atomicAdd(&f.counters->dda_steps, acc.dda_steps);
+        if (acc.columns_nonempty) atomicAdd(&f.counters->columns_nonempty, acc.columns_nonempty);
+        if (acc.runs_visited) atomicAdd(&f.counters->runs_visited, acc.runs_visited);
+        if (acc.px_voxel) atomicAdd(&f.counters->px_voxel, acc.px_voxel);
+        if (acc.px_sky) atomicAdd(&f.counters->px_sky, acc.px_sky);
+        if (gl == 0) atomicAdd(&f.counters->rays, 1ull);
     }
+#undef GBALLOT
+#undef GSHFL
 }
 
 // ---- Phase 2 -----------------------------------------------------------------------------------------------
@@ -682,12 +746,27 @@ __global__ void fill_kernel(uint32_t* dst, uint32_t value, int64_t n) {
 
 } // namespace
 
-cudaError_t cvxd_launch_phase1(const cvxd_world& world, const cvxd_frame& frame, cudaStream_t stream) {
-    int n = frame.ray_end - frame.ray_begin;
-    if (n <= 0) return cudaSuccess;
-    int blocks = (n + CVXD_WARPS_PER_CTA - 1) / CVXD_WARPS_PER_CTA;
-    phase1_kernel<<<blocks, CVXD_WARPS_PER_CTA * 32, 0, stream>>>(world, frame);
+template <int G>
+static cudaError_t launch_phase1_g(const cvxd_world& world, const cvxd_frame& frame, int n, cudaStream_t stream) {
+    constexpr int groupsPerCta = CVXD_THREADS_PER_CTA / G;
+    const int blocks = (n + groupsPerCta - 1) / groupsPerCta;
+    const int seenWords = ((frame.width > frame.height ? frame.width : frame.height) + 31) >> 5;
+    const size_t smem = (size_t)groupsPerCta * seenWords * sizeof(uint32_t);
+    if (frame.counters) phase1_kernel<G, true><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
+    else                phase1_kernel<G, false><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
     return cudaGetLastError();
+}
+
+// group_size: lanes per ray (8, 16, 32) or 0 = choose by ray count: few rays -> wide groups (the frame is bound by its
+// slowest ray), many rays -> narrow groups (more rays in flight per SM).
+cudaError_t cvxd_launch_phase1(const cvxd_world& world, const cvxd_frame& frame, int group_size, cudaStream_t stream) {
+    const int n = frame.ray_end - frame.ray_begin;
+    if (n <= 0) return cudaSuccess;
+    int g = group_size;
+    if (g != 8 && g != 16 && g != 32) g = n <= 2400 ? 32 : (n <= 4800 ? 16 : 8);
+    if (g == 32) return launch_phase1_g<32>(world, frame, n, stream);
+    if (g == 16) return launch_phase1_g<16>(world, frame, n, stream);
+    return launch_phase1_g<8>(world, frame, n, stream);
 }
 
 cudaError_t cvxd_launch_phase2(const cvxd_blit& blit, cudaStream_t stream) {

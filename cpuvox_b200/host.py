@@ -276,6 +276,24 @@ class RenderManager:
         self._ck(lib.cvx_last_draw_ms(self._ctx, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def set_option(self, option: int, value: int):
+        self._ck(lib.cvx_set_option(self._ctx, option, value))
+
+    def set_group_size(self, lanes: int):
+        """Lanes cooperating on one ray in Phase 1: 0 = auto (from the frame's ray count), 8, 16 or 32."""
+        self.set_option(N.OPT_GROUP_SIZE, lanes)
+
+    def set_counters(self, on: bool):
+        self.set_option(N.OPT_COUNTERS, int(on))
+
+    def profile_begin(self, max_draws: int):
+        self._ck(lib.cvx_profile_begin(self._ctx, max_draws))
+
+    def profile_end(self) -> Tuple[float, float, int]:
+        a, b, n = C.c_double(), C.c_double(), C.c_int32()
+        self._ck(lib.cvx_profile_end(self._ctx, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
     def launch_count(self) -> int:
         return int(lib.cvx_launch_count(self._ctx))
 

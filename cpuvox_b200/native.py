@@ -70,6 +70,8 @@ class Config(C.Structure):
 
 
 FLAG_COUNTERS = 1
+OPT_GROUP_SIZE = 1
+OPT_COUNTERS = 2
 
 
 class Pose(C.Structure):
@@ -128,6 +130,9 @@ SYMBOLS = {
     "cvx_set_external_frame": (C.c_int, [_P, _P]),
     "cvx_last_draw_ms": (C.c_int, [_P, C.POINTER(_F), C.POINTER(_F)]),
     "cvx_launch_count": (_I64, [_P]),
+    "cvx_set_option": (C.c_int, [_P, _I32, _I32]),
+    "cvx_profile_begin": (C.c_int, [_P, _I32]),
+    "cvx_profile_end": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I32)]),
     "cvx_debug_ray_setup": (C.c_int, [_P, C.POINTER(FrameSetup), C.POINTER(RayState), _I32]),
     "cvx_host_quat_euler": (None, [_F, _F, _F, C.POINTER(_F * 4)]),
     "cvx_host_limit_rotation_horizon": (None, [C.POINTER(Pose)]),

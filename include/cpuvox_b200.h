@@ -148,6 +148,18 @@ int cvx_last_draw_ms(cvx_ctx* ctx, float* out_phase1_ms, float* out_phase2_ms);
 /* Number of kernel launches issued by this context since creation. */
 int64_t cvx_launch_count(const cvx_ctx* ctx);
 
+/* Tuning / measurement knobs (no reference analogue).
+ *   CVX_OPT_GROUP_SIZE  lanes cooperating on one ray in Phase 1: 0 = choose per frame from the ray count, or 8, 16, 32.
+ *   CVX_OPT_COUNTERS    1 = accumulate cvx_counters (same as CVX_FLAG_COUNTERS at creation), 0 = off. */
+#define CVX_OPT_GROUP_SIZE 1
+#define CVX_OPT_COUNTERS 2
+int cvx_set_option(cvx_ctx* ctx, int32_t option, int32_t value);
+/* Device-side timing of many draws: after cvx_profile_begin every cvx_draw / cvx_draw_batch view records CUDA
+ * events around Phase 1 and Phase 2 on the context's stream (up to max_draws views); cvx_profile_end waits for
+ * them and returns the summed kernel durations in milliseconds and the number of views timed. */
+int cvx_profile_begin(cvx_ctx* ctx, int32_t max_draws);
+int cvx_profile_end(cvx_ctx* ctx, double* out_phase1_ms, double* out_phase2_ms, int32_t* out_draws);
+
 /* Debug: dump the per-ray state after RaySetupJob/DDASetupJob/TraceToFirstColumnJob
  * (DrawSegmentRayJob.cs:12-144) for every flat ray index; 16 x 4 bytes per ray, see cvx_ray_state. */
 typedef struct cvx_ray_state {

@@ -445,6 +445,8 @@ void fill_segment_contexts(const orc_frame_setup* s, int W, int H, SegCtx ctx[4]
 
 struct Counters {
     uint64_t dda_steps = 0, columns_nonempty = 0, runs_visited = 0, px_voxel = 0, px_sky = 0, rays = 0;
+    // diagnostics only (orc_ray_stats): work distribution along one ray
+    uint64_t columns_entered = 0, renarrows = 0, spans_tested = 0, spans_committed = 0, spans_wrote = 0;
 };
 
 struct RayCont { // RayContinuation, DrawSegmentRayJob.cs:146-153
@@ -636,6 +638,7 @@ void execute_ray(const orc_world* w, const SegCtx& sc, const Cam& cam, const Ray
         f3 camSpaceMaxNext = madd3(planeStartTopProjected, planeRayDirectionProjected, ray.dist.y);
 
         if (ray.dist.x > 2.0f && frustumDirMaxWorld == FLOAT_EPSILON) { // :295-422
+            cn.renarrows++;
             float clipLastMinLerp, clipLastMaxLerp, clipNextMinLerp, clipNextMaxLerp;
             bool clippedLast = world_bounds_clipping(camSpaceMinLast, camSpaceMaxLast, frustumBoundsMin, frustumBoundsMax, clipLastMinLerp, clipLastMaxLerp);
             bool clippedNext = world_bounds_clipping(camSpaceMinNext, camSpaceMaxNext, frustumBoundsMin, frustumBoundsMax, clipNextMinLerp, clipNextMaxLerp);
@@ -708,6 +711,7 @@ void execute_ray(const orc_world* w, const SegCtx& sc, const Cam& cam, const Ray
             if (nextFreePixelMin > nextFreePixelMax) { write_skybox(origMin, origMax, rayColumn, seen, cn); return; }
         }
 
+        cn.columns_entered++;
         float elementBoundsMin, elementBoundsMax;
         const RLEElement* elementPointer;
         const RLEElement* guardStart = world->elements + worldColumn.elementOffset; // ElementGuardStart World.cs:175-178
@@ -755,7 +759,10 @@ void execute_ray(const orc_world* w, const SegCtx& sc, const Cam& cam, const Ray
                     if (bf.x > bf.y) { std::swap(bf.x, bf.y); std::swap(uvA, uvB); }
                     int bMin = f2i(m_round(bf.x));
                     int bMax = f2i(m_round(bf.y));
+                    cn.spans_tested++;
                     if (bMax >= nextFreePixelMin && bMin <= nextFreePixelMax) {
+                        cn.spans_committed++;
+                        const uint64_t pxBefore = cn.px_voxel;
                         reduce_pixel_horizon(origMin, origMax, bMin, bMax, nextFreePixelMin, nextFreePixelMax, seen, frustumBoundsMin, frustumBoundsMax);
                         for (int y = bMin; y <= bMax; y++) {
                             if (seen[y] == 0) {
@@ -769,6 +776,7 @@ void execute_ray(const orc_world* w, const SegCtx& sc, const Cam& cam, const Ray
                                 cn.px_voxel++;
                             }
                         }
+                        if (cn.px_voxel != pxBefore) cn.spans_wrote++;
                         if (nextFreePixelMin > nextFreePixelMax) { write_skybox(origMin, origMax, rayColumn, seen, cn); return; }
                     }
                 }
@@ -793,7 +801,10 @@ void execute_ray(const orc_world* w, const SegCtx& sc, const Cam& cam, const Ray
                 float fx = m_round(secA.x / secA.z), fy = m_round(secB.x / secB.z);
                 int bMin = f2i(fx), bMax = f2i(fy);
                 if (bMin > bMax) std::swap(bMin, bMax);
+                cn.spans_tested++;
                 if (bMax >= nextFreePixelMin && bMin <= nextFreePixelMax) {
+                    cn.spans_committed++;
+                    const uint64_t pxBefore = cn.px_voxel;
                     reduce_pixel_horizon(origMin, origMax, bMin, bMax, nextFreePixelMin, nextFreePixelMax, seen, frustumBoundsMin, frustumBoundsMax);
                     for (int y = bMin; y <= bMax; y++) {
                         if (seen[y] == 0) {
@@ -803,6 +814,7 @@ void execute_ray(const orc_world* w, const SegCtx& sc, const Cam& cam, const Ray
                             cn.px_voxel++;
                         }
                     }
+                    if (cn.px_voxel != pxBefore) cn.spans_wrote++;
                     if (nextFreePixelMin > nextFreePixelMax) { write_skybox(origMin, origMax, rayColumn, seen, cn); return; }
                 }
             }
@@ -1093,6 +1105,33 @@ int orc_render_raybuffers(const orc_world* w, const orc_frame_setup* s, int32_t 
         }
     }
     return 0;
+}
+
+/* Diagnostics: per-ray work distribution, ORC_RAY_STAT_FIELDS uint64 per flat ray index:
+ * dda_steps, columns_nonempty, columns_entered, renarrows, runs_visited, spans_tested, spans_committed, spans_wrote,
+ * px_voxel, px_sky. Pixels go to scratch rows. */
+int orc_ray_stats(const orc_world* w, const orc_frame_setup* s, int32_t W, int32_t H, uint64_t* out, int32_t max_rays) {
+    if (!w || !s || !out) return -1;
+    SegCtx ctx[4]; int total;
+    fill_segment_contexts(s, W, H, ctx, total);
+    Cam cam = make_cam(s->camera);
+    int n = total < max_rays ? total : max_rays;
+    int nt = orc_hardware_threads();
+    std::vector<std::vector<uint8_t>> seen((size_t)nt);
+    std::vector<std::vector<uint32_t>> scratch((size_t)nt);
+    parallel_for(n, nt, [&](int i, int t) {
+        Counters cn;
+        RayCont rc;
+        scratch[t].resize((size_t)(W > H ? W : H));
+        if (setup_ray(w, s, ctx, cam, nullptr, nullptr, W, H, i, rc, cn, false, nullptr)) {
+            rc.rayColumn = scratch[t].data();
+            execute_ray(w, ctx[rc.segment], cam, rc, cam.inverse ? -1 : 1, seen[t], cn);
+        }
+        uint64_t* o = out + (size_t)i * ORC_RAY_STAT_FIELDS;
+        o[0] = cn.dda_steps; o[1] = cn.columns_nonempty; o[2] = cn.columns_entered; o[3] = cn.renarrows; o[4] = cn.runs_visited;
+        o[5] = cn.spans_tested; o[6] = cn.spans_committed; o[7] = cn.spans_wrote; o[8] = cn.px_voxel; o[9] = cn.px_sky;
+    });
+    return total;
 }
 
 /*

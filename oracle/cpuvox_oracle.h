@@ -105,6 +105,10 @@ int orc_blit(const orc_frame_setup* setup, int32_t width, int32_t height, const 
 /* Per-ray state after the three setup jobs (DrawSegmentRayJob.cs:12-144). */
 int orc_ray_setup(const orc_world* w, const orc_frame_setup* setup, int32_t width, int32_t height,
                   orc_ray_state* out, int32_t max_rays);
+/* Diagnostics: per-ray work counts (see the .cpp), ORC_RAY_STAT_FIELDS uint64 per ray. */
+#define ORC_RAY_STAT_FIELDS 10
+int orc_ray_stats(const orc_world* w, const orc_frame_setup* setup, int32_t width, int32_t height,
+                  uint64_t* out, int32_t max_rays);
 int orc_hardware_threads(void);
 
 #ifdef __cplusplus

@@ -78,6 +78,7 @@ def lib():
         L.orc_render_raybuffers.argtypes = [P, C.POINTER(FrameSetup), C.c_int32, C.c_int32, P, P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Counters)]
         L.orc_blit.argtypes = [C.POINTER(FrameSetup), C.c_int32, C.c_int32, P, P, P, C.c_int32, C.c_int32, C.c_int32]
         L.orc_ray_setup.argtypes = [P, C.POINTER(FrameSetup), C.c_int32, C.c_int32, P, C.c_int32]
+        L.orc_ray_stats.argtypes = [P, C.POINTER(FrameSetup), C.c_int32, C.c_int32, P, C.c_int32]
         L.orc_hardware_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -167,6 +168,19 @@ def ray_setup(world: OracleWorld, setup: FrameSetup, width, height) -> np.ndarra
     total = sum(max(0, setup.segments[k].ray_count) for k in range(4))
     out = np.zeros(max(1, total), dtype=RAY_STATE_DTYPE)
     n = lib().orc_ray_setup(world._w, C.byref(setup), width, height, out.ctypes.data_as(C.c_void_p), total)
+    assert n == total
+    return out[:total]
+
+
+RAY_STAT_FIELDS = ("dda_steps", "columns_nonempty", "columns_entered", "renarrows", "runs_visited", "spans_tested",
+                   "spans_committed", "spans_wrote", "px_voxel", "px_sky")
+
+
+def ray_stats(world: OracleWorld, setup: FrameSetup, width, height) -> np.ndarray:
+    """Diagnostics: per-ray work counts, shape (rays, len(RAY_STAT_FIELDS))."""
+    total = sum(max(0, setup.segments[k].ray_count) for k in range(4))
+    out = np.zeros((max(1, total), len(RAY_STAT_FIELDS)), dtype=np.uint64)
+    n = lib().orc_ray_stats(world._w, C.byref(setup), width, height, out.ctypes.data_as(C.c_void_p), total)
     assert n == total
     return out[:total]
 

@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--maxdim", type=int, default=1024)
     ap.add_argument("--synthetic", action="store_true")
     ap.add_argument("--no-oracle", action="store_true")
+    ap.add_argument("--group", type=int, default=0)
+    ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--out", default="gpurun_out/gpu_check.json")
     a = ap.parse_args()
     W, H = [int(x) for x in a.res.split("x")]
@@ -37,6 +39,7 @@ def main():
     rm = cv.RenderManager(0, counters=True)
     rm.upload_world(world)
     rm.set_resolution(W, H)
+    rm.set_group_size(a.group)
     ow = None if a.no_oracle else orc.OracleWorld(world.dims, world.blobs, world.column_counts)
     poses = cv.benchmark_path(world.dims, a.frames, far_clip=2.0 * world.max_dimension)
     results = []
@@ -48,11 +51,15 @@ def main():
         rm.sync()
         p1, p2 = rm.last_draw_ms()
         cn = rm.counters()
-        # warm timing (second run, counters still on)
-        rm.draw_setup(setup)
-        rm.sync()
-        q1, q2 = rm.last_draw_ms()
-        rm.counters()
+        # warm timing with the counters compiled out (the product configuration)
+        rm.set_counters(False)
+        q1 = q2 = 1e9
+        for _ in range(2):
+            rm.draw_setup(setup)
+            rm.sync()
+            t1, t2 = rm.last_draw_ms()
+            q1, q2 = min(q1, t1), min(q2, t2)
+        rm.set_counters(True)
         rec = {"frame": i, "rays": cn["rays"], "p1_ms": p1, "p2_ms": p2, "p1_warm_ms": q1, "p2_warm_ms": q2, "counters": cn}
         if ow is not None:
             frame = rm.read_frame()
@@ -70,12 +77,14 @@ def main():
             if not rec["counters_equal"]:
                 rec["oracle_counters"] = ocn
         results.append(rec)
-        print(json.dumps(rec), flush=True)
+        if a.verbose:
+            print(json.dumps(rec), flush=True)
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     with open(a.out, "w") as f:
         json.dump(results, f, indent=1)
     tot = sum(r["p1_warm_ms"] + r["p2_warm_ms"] for r in results)
-    print(f"mean frame {tot / len(results):.3f} ms -> {1000.0 * len(results) / tot:.1f} fps (warm, counters on)")
+    bad = [r["frame"] for r in results if r.get("td_mismatch") or r.get("lr_mismatch") or r.get("frame_mismatch") or not r.get("counters_equal", True)]
+    print(f"group {a.group}: mean frame {tot / len(results):.3f} ms -> {1000.0 * len(results) / tot:.1f} fps (warm, counters off); max p1 {max(r['p1_warm_ms'] for r in results):.3f} ms; parity-bad frames: {bad}")
 
 
 if __name__ == "__main__":
