@@ -18,3 +18,4 @@ from .host import (  # noqa: F401
     frame_setup,
     setup_lods,
 )
+from .parallel import ShardedRenderManager, broadcast_world, partition_rays, partition_views, ray_weights  # noqa: F401,E402

@@ -591,6 +591,35 @@ int cvx_debug_ray_setup(cvx_ctx* ctx, const cvx_frame_setup* setup, cvx_ray_stat
     return f.total_rays;
 }
 
+static_assert(CVX_IPC_HANDLE_BYTES == sizeof(cudaIpcMemHandle_t), "ipc handle size");
+
+int cvx_ipc_export_frame(cvx_ctx* ctx, uint8_t out_handle[CVX_IPC_HANDLE_BYTES]) {
+    if (!ctx || !out_handle) return CVX_ERR_INVALID_ARGUMENT;
+    if (ctx->width <= 0) return fail(ctx, CVX_ERR_NO_RESOLUTION, "no resolution set");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CU(ctx, cudaIpcGetMemHandle(&h, ctx->frames[0]));
+    memcpy(out_handle, &h, sizeof h);
+    return CVX_OK;
+}
+
+int cvx_ipc_open(cvx_ctx* ctx, const uint8_t handle[CVX_IPC_HANDLE_BYTES], void** out_device_ptr) {
+    if (!ctx || !handle || !out_device_ptr) return CVX_ERR_INVALID_ARGUMENT;
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    CU(ctx, cudaIpcOpenMemHandle(out_device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return CVX_OK;
+}
+
+int cvx_ipc_close(cvx_ctx* ctx, void* device_ptr) {
+    if (!ctx || !device_ptr) return CVX_ERR_INVALID_ARGUMENT;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaIpcCloseMemHandle(device_ptr));
+    return CVX_OK;
+}
+
 int cvx_alloc_pinned(int64_t bytes, void** out) {
     if (!out || bytes <= 0) return CVX_ERR_INVALID_ARGUMENT;
     cudaError_t e = cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault);

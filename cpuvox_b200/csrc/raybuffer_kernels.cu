@@ -757,13 +757,14 @@ static cudaError_t launch_phase1_g(const cvxd_world& world, const cvxd_frame& fr
     return cudaGetLastError();
 }
 
-// group_size: lanes per ray (8, 16, 32) or 0 = choose by ray count: few rays -> wide groups (the frame is bound by its
-// slowest ray), many rays -> narrow groups (more rays in flight per SM).
+// group_size: lanes per ray (8, 16, 32) or 0 = automatic. Measured on B200 (mill 1024^3, 1080p and 4K, 1920..12000 rays
+// per frame): the frame time is set by its slowest ray, and a full warp per ray has the shortest per-ray chain, so
+// automatic = 32; narrower groups only pay off when far more rays than resident warps are in flight.
 cudaError_t cvxd_launch_phase1(const cvxd_world& world, const cvxd_frame& frame, int group_size, cudaStream_t stream) {
     const int n = frame.ray_end - frame.ray_begin;
     if (n <= 0) return cudaSuccess;
     int g = group_size;
-    if (g != 8 && g != 16 && g != 32) g = n <= 2400 ? 32 : (n <= 4800 ? 16 : 8);
+    if (g != 8 && g != 16 && g != 32) g = 32;
     if (g == 32) return launch_phase1_g<32>(world, frame, n, stream);
     if (g == 16) return launch_phase1_g<16>(world, frame, n, stream);
     return launch_phase1_g<8>(world, frame, n, stream);

@@ -308,6 +308,24 @@ class RenderManager:
         self._ck(lib.cvx_device_frame(self._ctx, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    def set_stream(self, cuda_stream: int):
+        """Run on a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); 0 restores the own stream."""
+        self._ck(lib.cvx_set_stream(self._ctx, C.c_void_p(cuda_stream)))
+
+    def ipc_export_frame(self) -> bytes:
+        h = (C.c_uint8 * 64)()
+        self._ck(lib.cvx_ipc_export_frame(self._ctx, C.byref(h)))
+        return bytes(h)
+
+    def ipc_open(self, handle: bytes) -> int:
+        h = (C.c_uint8 * 64)(*handle)
+        p = C.c_void_p()
+        self._ck(lib.cvx_ipc_open(self._ctx, C.byref(h), C.byref(p)))
+        return p.value
+
+    def ipc_close(self, device_ptr: int):
+        self._ck(lib.cvx_ipc_close(self._ctx, C.c_void_p(device_ptr)))
+
     def set_external_frame(self, device_ptr: int):
         self._ck(lib.cvx_set_external_frame(self._ctx, C.c_void_p(device_ptr)))
 

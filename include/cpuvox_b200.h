@@ -160,8 +160,17 @@ int cvx_set_option(cvx_ctx* ctx, int32_t option, int32_t value);
 int cvx_profile_begin(cvx_ctx* ctx, int32_t max_draws);
 int cvx_profile_end(cvx_ctx* ctx, double* out_phase1_ms, double* out_phase2_ms, int32_t* out_draws);
 
+/* ---- multi-GPU, one process per GPU -------------------------------------------
+ * The root rank exports its internal framebuffer as a CUDA IPC handle; every other rank opens it and passes the mapped
+ * pointer to cvx_blit_owned, so Phase 2 stores each rank's pixels straight into the root's framebuffer over NVLink —
+ * the gather is the kernel's own stores, no staging copy and no collective on the data path. */
+#define CVX_IPC_HANDLE_BYTES 64
+int cvx_ipc_export_frame(cvx_ctx* ctx, uint8_t out_handle[CVX_IPC_HANDLE_BYTES]);
+int cvx_ipc_open(cvx_ctx* ctx, const uint8_t handle[CVX_IPC_HANDLE_BYTES], void** out_device_ptr);
+int cvx_ipc_close(cvx_ctx* ctx, void* device_ptr);
+
 /* Debug: dump the per-ray state after RaySetupJob/DDASetupJob/TraceToFirstColumnJob
- * (DrawSegmentRayJob.cs:12-144) for every flat ray index; 16 x 4 bytes per ray, see cvx_ray_state. */
+ * (DrawSegmentRayJob.cs:12-144) for every flat ray index; 18 x 4 bytes per ray, see cvx_ray_state. */
 typedef struct cvx_ray_state {
     int32_t segment;
     int32_t plane_ray_index;

@@ -1107,6 +1107,24 @@ int orc_render_raybuffers(const orc_world* w, const orc_frame_setup* s, int32_t 
     return 0;
 }
 
+/* Test hook: the DDA cell sequence of one ray exactly as ExecuteRay walks it (LOD switch at the top of every iteration,
+ * DrawSegmentRayJob.cs:237-243, then Step :613). Per step: cell x, cell z, lod, and the (last, next) distances. */
+int orc_dda_walk(const float start[2], const float dir[2], const float lod_distances[ORC_LOD_LEVELS], float far_clip,
+                 int32_t max_steps, int32_t* out_cells, float* out_dists) {
+    DDA d;
+    d.init(f2{start[0], start[1]}, f2{dir[0], dir[1]});
+    int lod = 0, voxelScale = 1, n = 0;
+    float lodMax = lod_distances[0];
+    while (n < max_steps) {
+        if (d.dist.x >= lodMax) { d.next_lod(voxelScale); lod++; voxelScale *= 2; lodMax = lod_distances[lod]; }
+        out_cells[3 * n] = d.position.x; out_cells[3 * n + 1] = d.position.y; out_cells[3 * n + 2] = lod;
+        out_dists[2 * n] = d.dist.x; out_dists[2 * n + 1] = d.dist.y;
+        n++;
+        if (d.do_step(far_clip)) break;
+    }
+    return n;
+}
+
 /* Diagnostics: per-ray work distribution, ORC_RAY_STAT_FIELDS uint64 per flat ray index:
  * dda_steps, columns_nonempty, columns_entered, renarrows, runs_visited, spans_tested, spans_committed, spans_wrote,
  * px_voxel, px_sky. Pixels go to scratch rows. */

@@ -105,6 +105,9 @@ int orc_blit(const orc_frame_setup* setup, int32_t width, int32_t height, const 
 /* Per-ray state after the three setup jobs (DrawSegmentRayJob.cs:12-144). */
 int orc_ray_setup(const orc_world* w, const orc_frame_setup* setup, int32_t width, int32_t height,
                   orc_ray_state* out, int32_t max_rays);
+/* Test hook: DDA cell sequence of one ray (3 ints per step: x, z, lod; 2 floats per step: last, next distance). */
+int orc_dda_walk(const float start[2], const float dir[2], const float lod_distances[ORC_LOD_LEVELS], float far_clip,
+                 int32_t max_steps, int32_t* out_cells, float* out_dists);
 /* Diagnostics: per-ray work counts (see the .cpp), ORC_RAY_STAT_FIELDS uint64 per ray. */
 #define ORC_RAY_STAT_FIELDS 10
 int orc_ray_stats(const orc_world* w, const orc_frame_setup* setup, int32_t width, int32_t height,

@@ -79,6 +79,7 @@ def lib():
         L.orc_blit.argtypes = [C.POINTER(FrameSetup), C.c_int32, C.c_int32, P, P, P, C.c_int32, C.c_int32, C.c_int32]
         L.orc_ray_setup.argtypes = [P, C.POINTER(FrameSetup), C.c_int32, C.c_int32, P, C.c_int32]
         L.orc_ray_stats.argtypes = [P, C.POINTER(FrameSetup), C.c_int32, C.c_int32, P, C.c_int32]
+        L.orc_dda_walk.argtypes = [C.POINTER(C.c_float * 2), C.POINTER(C.c_float * 2), C.POINTER(C.c_float * LODS), C.c_float, C.c_int32, P, P]
         L.orc_hardware_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -170,6 +171,16 @@ def ray_setup(world: OracleWorld, setup: FrameSetup, width, height) -> np.ndarra
     n = lib().orc_ray_setup(world._w, C.byref(setup), width, height, out.ctypes.data_as(C.c_void_p), total)
     assert n == total
     return out[:total]
+
+
+def dda_walk(start, direction, lod_distances, far_clip, max_steps=100000):
+    """Cell sequence (x, z, lod) and (last, next) distances of one ray as ExecuteRay walks it."""
+    cells = np.zeros((max_steps, 3), dtype=np.int32)
+    dists = np.zeros((max_steps, 2), dtype=np.float32)
+    n = lib().orc_dda_walk(C.byref((C.c_float * 2)(*start)), C.byref((C.c_float * 2)(*direction)),
+                           C.byref((C.c_float * LODS)(*[float(x) for x in lod_distances])), far_clip, max_steps,
+                           cells.ctypes.data_as(C.c_void_p), dists.ctypes.data_as(C.c_void_p))
+    return cells[:n], dists[:n]
 
 
 RAY_STAT_FIELDS = ("dda_steps", "columns_nonempty", "columns_entered", "renarrows", "runs_visited", "spans_tested",

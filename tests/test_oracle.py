@@ -1,0 +1,254 @@
+"""CPU tests of the oracle (oracle/cpuvox_oracle.cpp): hand-derived cases for each helper, the invariants the reference
+author checks by eye, and the committed golden fixtures. The reference has no tests of its own."""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import POSES, ROOT, crc, pose_for, setup_for
+from rle import encode_world
+
+SKY = 0x191919FF
+MAGENTA = 0xFF | (255 << 8) | (20 << 16) | (147 << 24)  # ColorARGB32(255,20,147), RenderManager.cs:58-92
+BIG = [1e9] * 6
+
+
+def test_dda_cells_are_pierced_by_the_ray(orc):
+    """SegmentDDAData (SegmentDDAData.cs:17-28,135-150) vs brute force: unit steps, every cell is crossed by the ray and
+    the (last, next) distances bracket the cell."""
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        start = rng.uniform(0.0, 64.0, 2).astype(np.float32)
+        ang = rng.uniform(0, 2 * np.pi)
+        d = np.array([np.cos(ang), np.sin(ang)], dtype=np.float32)
+        d /= np.float32(np.sqrt(np.float32(d[0] * d[0] + d[1] * d[1])))
+        cells, dists = orc.dda_walk(start, d, BIG, 300.0, 2000)
+        assert len(cells) > 250
+        assert (cells[0, :2] == np.floor(start)).all()
+        steps = np.abs(np.diff(cells[:, :2], axis=0))
+        assert (steps.sum(axis=1) == 1).all(), "one axis, one cell per step"
+        assert (dists[1:, 0] == dists[:-1, 1]).all() or np.allclose(dists[1:, 0], dists[:-1, 1], rtol=0, atol=0), "next of step i is last of step i+1"
+        mid = 0.5 * (dists[:, 0].astype(np.float64) + dists[:, 1])
+        p = start.astype(np.float64)[None, :] + mid[:, None] * d.astype(np.float64)[None, :]
+        inside = (p >= cells[:, :2] - 1e-3) & (p <= cells[:, :2] + 1 + 1e-3)
+        assert inside.all()
+        assert (dists[:, 1] >= dists[:, 0]).all()
+
+
+def test_dda_axis_aligned_and_sign_zero(orc):
+    """sign(0) = 0: a ray along +x never steps in z (tDelta = 1e7 on the dead axis), SegmentDDAData.cs:22-27."""
+    cells, dists = orc.dda_walk((3.25, 7.5), (1.0, 0.0), BIG, 40.0, 100)
+    assert (cells[:, 1] == 7).all() and (np.diff(cells[:, 0]) == 1).all()
+    np.testing.assert_allclose(dists[1:, 0], np.arange(len(cells) - 1) + 0.75, rtol=1e-6)
+    cells, _ = orc.dda_walk((3.25, 7.5), (0.0, -1.0), BIG, 5.0, 100)
+    assert (cells[:, 0] == 3).all() and (np.diff(cells[:, 1]) == -1).all()
+
+
+def test_dda_lod_switch_alignment(orc):
+    """NextLOD (SegmentDDAData.cs:31-73): after a switch the cell is aligned to the coarser grid, still contains the ray,
+    and the switch happens at the first step whose last-distance reaches the LOD distance."""
+    rng = np.random.default_rng(11)
+    lods = [20.0, 45.0, 100.0, 220.0, 500.0, 1e9]
+    for _ in range(100):
+        start = rng.uniform(100.0, 200.0, 2).astype(np.float32)
+        ang = rng.uniform(0, 2 * np.pi)
+        d = np.array([np.cos(ang), np.sin(ang)], dtype=np.float32)
+        cells, dists = orc.dda_walk(start, d, lods, 800.0, 4000)
+        lod = cells[:, 2]
+        assert (np.diff(lod) >= 0).all() and lod.max() >= 4
+        size = 1 << lod
+        assert ((cells[:, 0] % size) == 0).all() and ((cells[:, 1] % size) == 0).all()
+        mid = 0.5 * (dists[:, 0].astype(np.float64) + dists[:, 1])
+        p = start.astype(np.float64)[None, :] + mid[:, None] * d.astype(np.float64)[None, :]
+        tol = 2e-2
+        assert ((p >= cells[:, :2] - tol) & (p <= cells[:, :2] + size[:, None] + tol)).all()
+        for j in range(5):
+            first = int(np.argmax(lod > j))  # first step walked at a LOD coarser than j
+            assert first > 0
+            # the test of :237 sees the distance crossed by the previous Step, i.e. the previous step's `next`
+            assert dists[first - 1, 1] >= lods[j]
+            assert (dists[:first - 1, 1] < lods[j]).all()
+
+
+def test_segment_setup_closed_forms(cv, orc, terrain_world):
+    """VP on screen => RayCounts 2(H-vy), 2vy, 2(W-vx), 2vx (RenderManager.cs:416-434,482-483), and the product's host
+    setup equals the oracle's restatement bit for bit."""
+    W, H = 640, 360
+    for spec in POSES:
+        s = setup_for(cv, terrain_world, spec, W, H)
+        vx, vy = s.vanishing_point_screen
+        if 0 <= vx <= W and 0 <= vy <= H:
+            rc = [s.segments[k].ray_count for k in range(4)]
+            exp = [2 * (H - vy), 2 * vy, 2 * (W - vx), 2 * vx]
+            assert all(abs(a - b) <= 1 for a, b in zip(rc, exp)), (spec[0], rc, exp)
+            assert abs(sum(rc) - (2 * W + 2 * H)) <= 2
+        tdr = max(0, s.segments[0].ray_count) + max(0, s.segments[1].ray_count)
+        lrr = max(0, s.segments[2].ray_count) + max(0, s.segments[3].ray_count)
+        assert tdr <= W + 2 * H and lrr <= 2 * W + H, "raybuffer row bounds, RenderManager.cs:35-36"
+        pose = pose_for(cv, terrain_world, spec)
+        o = orc.frame_setup(pose.position, pose.rotation, W, H, cv.setup_lods(256, W, H), 256, far=pose.far_clip)
+        assert bytes(o) == bytes(s), spec[0]
+
+
+def _render(orc, ow, s, W, H, fill=0, **kw):
+    td = np.full((W + 2 * H, H), fill, dtype=np.uint32)
+    lr = np.full((2 * W + H, W), fill, dtype=np.uint32)
+    return orc.render_raybuffers(ow, orc.copy_setup(s), W, H, td=td, lr=lr, **kw)
+
+
+def _segment_ranges(s, W, H):
+    """(buffer, first row, rows, pixMin, pixMax) per active segment, RenderManager.cs:281-318."""
+    out = []
+    vx, vy = s.vanishing_point_screen
+    rnd = lambda v, n: int(min(max(np.rint(np.float32(v)), 0), n - 1))
+    for k in range(4):
+        rc = s.segments[k].ray_count
+        if rc <= 0:
+            continue
+        off = s.segments[0].ray_count if k == 1 else (s.segments[2].ray_count if k == 3 else 0)
+        if k < 2:
+            v = rnd(vy, H)
+            out.append((0, off, rc, v if k == 0 else 0, H - 1 if k == 0 else v))
+        else:
+            v = rnd(vx, W)
+            out.append((1, off, rc, 0 if k == 3 else v, v if k == 3 else W - 1))
+    return out
+
+
+@pytest.mark.parametrize("world_name", ["terrain_world", "structure_world", "mill_world"])
+def test_every_writable_pixel_written_exactly_once(cv, orc, request, world_name):
+    """Render modes 2/3 of the reference clear the raybuffer to magenta (UnityManager.cs:129-134): afterwards every pixel
+    of [originalNextFreePixelMin, Max] of every active row is voxel colour or skybox, nothing else is touched, and the
+    write counters add up to exactly that many pixels."""
+    world = request.getfixturevalue(world_name)
+    ow = orc.OracleWorld(world.dims, world.blobs, world.column_counts)
+    W, H = 320, 180
+    for spec in POSES:
+        s = setup_for(cv, world, spec, W, H)
+        td, lr, cn = _render(orc, ow, s, W, H, fill=MAGENTA)
+        touched = [np.zeros_like(td, dtype=bool), np.zeros_like(lr, dtype=bool)]
+        total = 0
+        for buf, off, rc, mn, mx in _segment_ranges(s, W, H):
+            touched[buf][off:off + rc, mn:mx + 1] = True
+            total += rc * (mx - mn + 1)
+        for buf, arr in enumerate((td, lr)):
+            assert (arr[touched[buf]] != MAGENTA).all(), spec[0]
+            assert (arr[~touched[buf]] == MAGENTA).all(), spec[0]
+        assert cn["px_voxel"] + cn["px_sky"] == total, spec[0]
+        assert cn["rays"] == sum(max(0, s.segments[k].ray_count) for k in range(4))
+
+
+def test_front_to_back_first_writer_wins(cv, orc, mill_world):
+    """A ray cut short by a nearer far clip executes a prefix of the full ray: whatever voxel pixels it wrote are final."""
+    world = mill_world
+    ow = orc.OracleWorld(world.dims, world.blobs, world.column_counts)
+    W, H = 320, 180
+    lods = cv.setup_lods(world.max_dimension, W, H)
+    for spec in POSES[:5]:
+        pose = pose_for(cv, world, spec)
+        full = cv.frame_setup(pose, W, H, lods, world.dims[1])
+        td_f, lr_f, _ = _render(orc, ow, full, W, H)
+        for far in (40.0, 90.0, 200.0):
+            cut = orc.copy_setup(full)
+            cut.camera.far_clip = far
+            td_c, lr_c, _ = _render(orc, ow, cut, W, H)
+            for a, b in ((td_c, td_f), (lr_c, lr_f)):
+                m = (a != SKY) & (a != 0)
+                assert (a[m] == b[m]).all()
+
+
+def test_thread_count_and_ray_ranges_do_not_change_results(cv, orc, terrain_world):
+    world = terrain_world
+    ow = orc.OracleWorld(world.dims, world.blobs, world.column_counts)
+    W, H = 333, 217
+    s = setup_for(cv, world, POSES[0], W, H)
+    td1, lr1, c1 = _render(orc, ow, s, W, H, threads=1)
+    td4, lr4, c4 = _render(orc, ow, s, W, H, threads=4)
+    assert np.array_equal(td1, td4) and np.array_equal(lr1, lr4) and c1 == c4
+    total = c1["rays"]
+    td = np.zeros_like(td1); lr = np.zeros_like(lr1)
+    parts = [0, total // 3, total // 2 + 7, total]
+    sums = {k: 0 for k in c1}
+    for a, b in zip(parts[:-1], parts[1:]):
+        _, _, c = orc.render_raybuffers(ow, orc.copy_setup(s), W, H, ray_begin=a, ray_end=b, td=td, lr=lr)
+        for k in c:
+            sums[k] += c[k]
+    assert np.array_equal(td, td1) and np.array_equal(lr, lr1) and sums == c1
+    f_full = orc.blit(orc.copy_setup(s), W, H, td1, lr1)
+    f_rows = np.zeros_like(f_full)
+    for a, b in ((0, 50), (50, 51), (51, H)):
+        orc.blit(orc.copy_setup(s), W, H, td1, lr1, row_begin=a, row_end=b, frame=f_rows)
+    assert np.array_equal(f_full, f_rows)
+    assert (f_full != 0).all(), "the segment triangles tile the screen (RenderManager.cs:114-117)"
+
+
+def test_empty_world_is_all_skybox(cv, orc):
+    dims = (64, 32, 64)
+    blob, cc = encode_world(np.zeros(dims, dtype=np.uint32))
+    ow = orc.OracleWorld(dims, [blob], [cc])
+    W, H = 160, 90
+    lods = np.full(6, 1e9, dtype=np.float32)
+    for spec in POSES[:4]:
+        pose = cv.CameraPose.from_euler(tuple(spec[2][i] * dims[i] for i in range(3)), spec[1], far_clip=128.0)
+        s = cv.frame_setup(pose, W, H, lods, dims[1])
+        td, lr, cn = _render(orc, ow, s, W, H)
+        assert cn["px_voxel"] == 0 and cn["runs_visited"] == 0 and cn["columns_nonempty"] == 0
+        frame = orc.blit(orc.copy_setup(s), W, H, td, lr)
+        assert (frame == SKY).all()
+
+
+def test_single_column_orientation_and_colours(cv, orc):
+    """One column, three voxels, three colours: seen from the side the frame shows them bottom to top in world order,
+    with sky above/below; from above only the top colour (cap) and the sides."""
+    dims = (32, 32, 32)
+    grid = np.zeros(dims, dtype=np.uint32)
+    c_bot, c_mid, c_top = 0x0000FFFF, 0x00FF00FF, 0xFF0000FF  # a=255 + one channel each
+    grid[16, 9, 16], grid[16, 10, 16], grid[16, 11, 16] = c_bot, c_mid, c_top
+    blob, cc = encode_world(grid)
+    ow = orc.OracleWorld(dims, [blob], [cc])
+    W, H = 320, 180
+    lods = np.full(6, 1e9, dtype=np.float32)
+    pose = cv.CameraPose.from_euler((16.5, 10.5, 4.0), (0.0, 0.0, 0.0), far_clip=64.0)  # looking along +z at the column
+    s = cv.frame_setup(pose, W, H, lods, dims[1])
+    td, lr, cn = _render(orc, ow, s, W, H)
+    frame = orc.blit(orc.copy_setup(s), W, H, td, lr)
+    col = frame[:, W // 2]
+    seq = [int(c) for i, c in enumerate(col) if c != SKY and (i == 0 or col[i - 1] != c)]
+    assert seq == [c_bot, c_mid, c_top], [hex(v) for v in seq]
+    assert cn["px_voxel"] > 0 and cn["columns_nonempty"] > 0
+    # each voxel is ~1/12.5 of the view distance tall: roughly equal bands
+    bands = [int((col == c).sum()) for c in (c_bot, c_mid, c_top)]
+    assert max(bands) - min(bands) <= 2 and min(bands) >= 5, bands
+    # from straight above (pitch 89): the top cap colour dominates
+    pose = cv.CameraPose.from_euler((16.5, 24.0, 16.5), (89.0, 0.0, 0.0), far_clip=64.0)
+    s = cv.frame_setup(pose, W, H, lods, dims[1])
+    td, lr, _ = _render(orc, ow, s, W, H)
+    frame = orc.blit(orc.copy_setup(s), W, H, td, lr)
+    vals, counts = np.unique(frame[frame != SKY], return_counts=True)
+    assert len(vals) and int(vals[np.argmax(counts)]) == c_top
+
+
+def test_oracle_matches_golden_fixtures(cv, orc, terrain_world, structure_world, mill_world):
+    """tests/golden/golden_v1.json (tests/golden/make_golden.py): pins the restatement, the world builders and the host
+    setup. The reference itself ships no vectors (parity unpinned by the reference)."""
+    with open(os.path.join(ROOT, "tests", "golden", "golden_v1.json")) as f:
+        golden = json.load(f)["worlds"]
+    worlds = {"terrain256": terrain_world, "structure512x128x256": structure_world, "mill256": mill_world}
+    specs = {p[0]: p for p in POSES}
+    for name, g in golden.items():
+        w = worlds[name]
+        assert list(w.dims) == g["dims"] and [crc(b) for b in w.blobs] == g["blob_crcs"], f"world builder output changed: {name}"
+        assert list(w.voxel_counts) == g["voxel_counts"]
+        ow = orc.OracleWorld(w.dims, w.blobs, w.column_counts)
+        for c in g["cases"]:
+            W, H = c["width"], c["height"]
+            s = setup_for(cv, w, specs[c["pose"]], W, H)
+            assert [s.segments[k].ray_count for k in range(4)] == c["ray_counts"]
+            assert [float(s.vanishing_point_screen[0]), float(s.vanishing_point_screen[1])] == c["vanishing_point"]
+            td, lr, cn = _render(orc, ow, s, W, H)
+            frame = orc.blit(orc.copy_setup(s), W, H, td, lr)
+            assert cn == c["counters"], (name, c["pose"], W, H)
+            assert (crc(td), crc(lr), crc(frame)) == (c["td_crc"], c["lr_crc"], c["frame_crc"]), (name, c["pose"], W, H)
