@@ -591,6 +591,29 @@ int cvx_debug_ray_setup(cvx_ctx* ctx, const cvx_frame_setup* setup, cvx_ray_stat
     return f.total_rays;
 }
 
+int cvx_debug_ray_timing(cvx_ctx* ctx, const cvx_frame_setup* setup, int64_t* out_cycles, int32_t max_rays) {
+    int r = check_ready(ctx, setup);
+    if (r) return r;
+    if (!out_cycles || max_rays < 0) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "bad output buffer");
+    cvxd_frame f;
+    make_frame(ctx, setup, f);
+    if ((r = validate_setup(ctx, setup, f.total_rays))) return r;
+    const int n = f.total_rays < max_rays ? f.total_rays : max_rays;
+    if (n == 0) return f.total_rays;
+    CU(ctx, cudaSetDevice(ctx->device));
+    long long* d = nullptr;
+    const size_t bytes = sizeof(long long) * CVXD_TIMING_REGIONS * (size_t)f.total_rays;
+    CU(ctx, cudaMalloc(&d, bytes));
+    f.timing = d; f.counters = nullptr;
+    cudaError_t e = cudaMemsetAsync(d, 0, bytes, ctx->stream);
+    if (e == cudaSuccess) { e = cvxd_launch_phase1(ctx->world, f, 32, ctx->stream); ctx->launches++; }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_cycles, d, sizeof(long long) * CVXD_TIMING_REGIONS * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, CVX_ERR_CUDA, "ray timing failed: %s", cudaGetErrorString(e));
+    return f.total_rays;
+}
+
 static_assert(CVX_IPC_HANDLE_BYTES == sizeof(cudaIpcMemHandle_t), "ipc handle size");
 
 int cvx_ipc_export_frame(cvx_ctx* ctx, uint8_t out_handle[CVX_IPC_HANDLE_BYTES]) {

@@ -9,6 +9,7 @@
 #define CVXD_LODS 6
 #define CVXD_MAX_AXIS 8192          /* longest raybuffer row (max(W,H)) the seen-mask in shared memory supports */
 #define CVXD_THREADS_PER_CTA 128
+#define CVXD_TIMING_REGIONS 8
 
 /* Device copy of one World LOD (Assets/Code/World.cs:8-43,161-188). Headers are transcoded at upload from the
  * reference's 12-byte RLEColumn into one 16-byte aligned uint4 per column so a lane fetches a column header with
@@ -60,6 +61,7 @@ struct cvxd_frame {
     uint32_t* td;                   /* top/down raybuffer: rows of `height` pixels */
     uint32_t* lr;                   /* left/right raybuffer: rows of `width` pixels */
     cvxd_counters* counters;        /* may be null */
+    long long* timing;              /* debug: CVXD_TIMING_REGIONS cycle counts per flat ray, or null */
 };
 
 struct cvxd_blit {

@@ -305,8 +305,11 @@ __device__ __forceinline__ void touch(const uint32_t* p) {
  * Neighbouring rows (adjacent rays of one segment) share a warp: they walk nearly the same columns, so the groups of
  * a warp stay mostly convergent while the number of rays in flight per SM grows by 32/G.
  */
-template <int G, bool COUNTERS>
-__global__ void __launch_bounds__(CVXD_THREADS_PER_CTA)
+#ifndef CVXD_MIN_CTAS_PER_SM
+#define CVXD_MIN_CTAS_PER_SM 4
+#endif
+template <int G, bool COUNTERS, bool TIMING>
+__global__ void __launch_bounds__(CVXD_THREADS_PER_CTA, CVXD_MIN_CTAS_PER_SM)
 phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ cvxd_frame f) {
     extern __shared__ uint32_t seen_all[];
     constexpr int GROUPS_PER_CTA = CVXD_THREADS_PER_CTA / G;
@@ -321,6 +324,12 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
 #define GBALLOT(p) ((__ballot_sync(gmask, (p)) >> gshift) & GBITS)
 #define GSHFL(v, src) __shfl_sync(gmask, (v), (src), G)
 
+    // TIMING builds (cvx_debug_ray_timing): cycles per code region of this ray, STAMP(r) closes the current region
+    long long tAcc[CVXD_TIMING_REGIONS] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tPrev = TIMING ? clock64() : 0;
+    int tCur = 0;
+#define STAMP(r) do { if (TIMING) { const long long t_ = clock64(); tAcc[tCur] += t_ - tPrev; tPrev = t_; tCur = (r); } } while (0)
+
     RaySetup rs;
     setup_ray(world, f, flat, rs);
     if (rs.status < 0) return;
@@ -332,7 +341,8 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
     Acc acc = {0, 0, 0, 0, 0}; // per lane; summed with atomics at the end (COUNTERS only)
     if (COUNTERS && gl == 0) acc.dda_steps = (unsigned long long)rs.lod_steps;
     RowState rw;
-    rw.seen = seen_all + group * seenWords;
+    rw.seen = seen_all + group * (seenWords + G);
+    int* scratch = (int*)(rw.seen + seenWords); // G ints: lane of a round -> batch cell of its column
     rw.row = row;
     rw.orig_min = sg.pix_min; rw.orig_max = sg.pix_max;
     rw.nf_min = rw.orig_min; rw.nf_max = rw.orig_max;
@@ -374,6 +384,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
         bool terminated = false; // ray ended inside the loop: skybox the rest and stop
         bool reachedEnd = false; // far clip or world exit
         while (!terminated && !reachedEnd) {
+            STAMP(1);
             // ---- look ahead: up to G cells of the DDA, lane i of the group keeps cell i -------------------------
             int n = 0, endKind = 0; // 1 = next cell is outside the world, 2 = far clip crossed after the last cell
             int myLod = 0, myIdx = 0; float myDl = 0.0f, myDn = 0.0f;
@@ -400,7 +411,18 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
             uint32_t remaining = GBALLOT(myNonEmpty);
             int cellsDone = n + (endKind == 1 ? 1 : 0); // the out-of-world probe counts as a step
 
+            // Round cache: span geometry of several consecutive columns of this batch, one run per lane (see form_round below).
+            uint32_t roundCols = 0u;      // batch cells whose runs are cached in the lanes
+            uint32_t roundInvalid = 0u;   // lanes holding an invalid element (Length == 0), which ends its column (:445-447)
+            int myBase = 0;               // batch lane c: first round lane of column c
+            // per-lane cached run: element fields, world-Y bounds, side span and cap span (none of it depends on the written-pixel state)
+            int r_ci = 0, r_len = 0, r_sMin = 0, r_sMax = 0, r_cMin = 0, r_cMax = 0, r_capIdx = 0, r_capKind = 0;
+            bool r_sideClip = false, r_capClip = false;
+            float r_eMin = 0.0f, r_eMax = 0.0f, r_bfx = 0.0f, r_bfy = 0.0f, r_uvAx = 0.0f, r_uvAy = 0.0f, r_uvBx = 0.0f, r_uvBy = 0.0f;
+            const int myRunCount = (int)(hdr.y & 0xffffu);
+
             while (remaining) {
+                STAMP(2);
                 // ---- next column that is not culled by the narrowed frustum (:261-281), found for all columns at once ----
                 int c;
                 float worldBoundsMin = 0.0f, worldBoundsMax = worldMaxY;
@@ -432,7 +454,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                 const float distNext = GSHFL(myDn, c);
                 const int cLod = GSHFL(myLod, c);
                 const uint32_t hOff = GSHFL(hdr.x, c);
-                const int runCount = (int)(GSHFL(hdr.y, c) & 0xffffu);
+                const int runCount = GSHFL(myRunCount, c);
                 const int cScale = 1 << cLod;
 
                 // :289-293
@@ -442,6 +464,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                 const F3 maxNext = F3{planeTop.x + planeDir.x * distNext, planeTop.y + planeDir.y * distNext, planeTop.z + planeDir.z * distNext};
 
                 if (distLast > 2.0f && frustumDirMaxWorld == EPS) { // re-narrow the frustum :295-422
+                    STAMP(3);
                     // The four clip parameters (last/next line x min/max end) and their projections are independent:
                     // lane L&3 of the group computes one of them (same operations as CameraData.cs:50-121), then they are shared.
                     const int L = gl & 3;
@@ -503,9 +526,182 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                     if (rw.nf_min > rw.nf_max) { terminated = true; cellsDone = c + 1; break; }
                 }
 
-                // ---- runs of this column, G per pass, in iteration order (:424-611) ----------------------------
                 const uint32_t* colBase = world.lods[cLod].elements + hOff;   // ElementGuardStart World.cs:175-178
                 const uint32_t* colColors = colBase + runCount + 2;           // ColorPointer :185-188
+
+                if (runCount <= G) {
+                    // ================= round path: columns of at most G runs =================================================
+                    STAMP(4);
+                    if (!((roundCols >> c) & 1u)) {
+                        // ---- form a round: this column plus the following columns that are likely to be entered, as long as
+                        // their runs fit in the G lanes. One run per lane: fetch, world-Y bounds (segmented prefix sum), and
+                        // the projected side/cap spans — the float-heavy part — once for all of them.
+                        uint32_t follow = remaining;
+                        if (frustumDirMaxWorld != EPS) {
+                            const float distTop = frustumDirMaxWorld > 0.0f ? myDn : myDl;
+                            const float distBot = frustumDirMinWorld < 0.0f ? myDn : myDl;
+                            const float newMax = camY + frustumDirMaxWorld * distTop;
+                            const float newMin = camY + frustumDirMinWorld * distBot;
+                            follow &= GBALLOT(myNonEmpty && !(myWorldMin > newMax || myWorldMax < newMin));
+                        }
+                        const uint32_t consider = (1u << c) | follow;
+                        const int v = ((consider >> gl) & 1u) ? myRunCount : 0;
+                        int incl = v;
+#pragma unroll
+                        for (int o = 1; o < G; o <<= 1) { int t = __shfl_up_sync(gmask, incl, o, G); if (gl >= o) incl += t; }
+                        const bool inRound = ((consider >> gl) & 1u) && incl <= G;
+                        roundCols = GBALLOT(inRound);
+                        myBase = incl - v;
+                        if (inRound) scratch[myBase] = gl;           // first lane of each cached column -> its batch cell
+                        const uint32_t startMask = __reduce_or_sync(gmask, inRound ? (1u << myBase) : 0u);
+                        const int totalRuns = GSHFL(incl, 31 - __clz(roundCols));
+                        __syncwarp(gmask);
+                        const int myStart = 31 - __clz(startMask & ((2u << gl) - 1u)); // lane 0 always starts a column
+                        const bool hasRun = gl < totalRuns;
+                        const int myCol = hasRun ? scratch[myStart] : c;
+                        const int k = gl - myStart;
+                        __syncwarp(gmask);
+                        const float cDl = GSHFL(myDl, myCol), cDn = GSHFL(myDn, myCol);
+                        const int colLod = GSHFL(myLod, myCol);
+                        const uint32_t colOff = GSHFL(hdr.x, myCol);
+                        const int colRuns = GSHFL(myRunCount, myCol);
+                        uint32_t el = 0u;
+                        if (hasRun) el = __ldg(world.lods[colLod].elements + colOff + (ITER > 0 ? 1 + k : colRuns - k));
+                        r_ci = (int)(short)(el & 0xffffu); r_len = (int)(short)(el >> 16); // RLEElement World.cs:245-259
+                        roundInvalid = GBALLOT(hasRun && r_len == 0);
+                        // lanes of my column from its start up to me, and whether an invalid element precedes me there
+                        const uint32_t mineUpToMe = ((2u << gl) - 1u) & ~((1u << myStart) - 1u);
+                        const bool valid = hasRun && !(roundInvalid & mineUpToMe);
+                        const int span = valid ? r_len * (1 << colLod) : 0;
+                        int sum = span;
+#pragma unroll
+                        for (int o = 1; o < G; o <<= 1) { int t = __shfl_up_sync(gmask, sum, o, G); if (gl >= o) sum += t; }
+                        const int before = GSHFL(sum, myStart > 0 ? myStart - 1 : 0);
+                        const int inclCol = sum - (myStart > 0 ? before : 0); // runs of my column up to and including me
+                        if (ITER > 0) { r_eMax = (float)(world.dim_y - (inclCol - span)); r_eMin = (float)(world.dim_y - inclCol); } // :449-455
+                        else          { r_eMin = (float)(inclCol - span); r_eMax = (float)inclCol; }
+
+                        STAMP(5);
+                        const F3 lMinLast = F3{planeBottom.x + planeDir.x * cDl, planeBottom.y + planeDir.y * cDl, planeBottom.z + planeDir.z * cDl};
+                        const F3 lMinNext = F3{planeBottom.x + planeDir.x * cDn, planeBottom.y + planeDir.y * cDn, planeBottom.z + planeDir.z * cDn};
+                        const F3 lMaxLast = F3{planeTop.x + planeDir.x * cDl, planeTop.y + planeDir.y * cDl, planeTop.z + planeDir.z * cDl};
+                        const F3 lMaxNext = F3{planeTop.x + planeDir.x * cDn, planeTop.y + planeDir.y * cDn, planeTop.z + planeDir.z * cDn};
+                        r_sideClip = false; r_capClip = false; r_capKind = 0;
+                        {
+                            const float portionBottom = unlerpf(0.0f, worldMaxY, r_eMin); // :478-481
+                            const float portionTop = unlerpf(0.0f, worldMaxY, r_eMax);
+                            F3 frontBottom = lerp3(lMinLast, lMaxLast, portionBottom);
+                            F3 frontTop = lerp3(lMinLast, lMaxLast, portionTop);
+                            float uA = (float)r_len, uB = 0.0f;
+                            if (clip_near_u(frontBottom, frontTop, uA, uB)) { // :489-502 (clips frontBottom/Top in place)
+                                r_uvAx = 1.0f / frontBottom.z; r_uvAy = uA / frontBottom.z;
+                                r_uvBx = 1.0f / frontTop.z;    r_uvBy = uB / frontTop.z;
+                                r_bfx = frontBottom.x / frontBottom.z; r_bfy = frontTop.x / frontTop.z;
+                                if (r_bfx > r_bfy) {
+                                    float t = r_bfx; r_bfx = r_bfy; r_bfy = t;
+                                    t = r_uvAx; r_uvAx = r_uvBx; r_uvBx = t;
+                                    t = r_uvAy; r_uvAy = r_uvBy; r_uvBy = t;
+                                }
+                                r_sMin = f2i(rintf(r_bfx)); r_sMax = f2i(rintf(r_bfy));
+                                r_sideClip = true;
+                            }
+                            F3 secA = frontTop, secB = frontTop; // :544-565; which cap, if any, depends on the camera height only
+                            if (portionTop < cameraPosYNormalized) { r_capKind = 1; r_capIdx = r_ci; secA = lerp3(lMinNext, lMaxNext, portionTop); secB = frontTop; }
+                            else if (portionBottom > cameraPosYNormalized) { r_capKind = 2; r_capIdx = r_ci + r_len - 1; secA = lerp3(lMinNext, lMaxNext, portionBottom); secB = frontBottom; }
+                            if (r_capKind && clip_near(secA, secB)) { // :568-578
+                                r_cMin = f2i(rintf(secA.x / secA.z)); r_cMax = f2i(rintf(secB.x / secB.z));
+                                if (r_cMin > r_cMax) { int t = r_cMin; r_cMin = r_cMax; r_cMax = t; }
+                                r_capClip = true;
+                            }
+                        }
+                        STAMP(4);
+                    }
+
+                    // ---- resolve column c against the current frustum / written-pixel state (:441-611) --------------------
+                    const int base = GSHFL(myBase, c);
+                    const uint32_t colMask = (runCount >= 32 ? FULL_MASK : ((1u << runCount) - 1u)) << base;
+                    const bool inCol = (colMask >> gl) & 1u;
+                    const uint32_t invalidHere = roundInvalid & colMask;
+                    const int endValid = invalidHere ? __ffs(invalidHere) - 1 : base + runCount; // first lane past the valid runs
+                    const bool valid = inCol && gl < endValid;
+                    const bool solid = valid && r_ci >= 0; // !IsAir
+                    const bool above = r_eMin > worldBoundsMax, below = r_eMax < worldBoundsMin;
+                    const bool isBreak = solid && (ITER > 0 ? (!above && below) : above); // :461-475 (above is tested first)
+                    const uint32_t breakMask = GBALLOT(isBreak);
+                    const int endVisit = breakMask ? __ffs(breakMask) : endValid;           // the breaking run itself was dereferenced
+                    const bool active = solid && gl < endVisit && !above && !below;
+                    const bool sideOk = active && r_sideClip;
+                    const bool capOk = active && r_capClip &&
+                                       (r_capKind == 1 ? !(r_eMax > worldBoundsMax) : !(r_eMin < worldBoundsMin)); // :549-565
+
+                    STAMP(6);
+                    // ---- commit, in reference order, only the spans that still hold an unwritten pixel ----------
+                    uint32_t pending = GBALLOT(sideOk || capOk);
+                    int visitedHere = endVisit - base;
+                    while (pending) {
+                        const bool wSide = sideOk && span_would_write(rw, r_sMin, r_sMax);
+                        const bool wCap = capOk && span_would_write(rw, r_cMin, r_cMax);
+                        const uint32_t hot = GBALLOT(wSide || wCap) & pending;
+                        if (!hot) break;
+                        const int j = __ffs(hot) - 1;
+                        pending &= ~((2u << j) - 1u);
+                        if (GSHFL((int)wSide, j)) { // side of run j :505-540
+                            int bMin = GSHFL(r_sMin, j), bMax = GSHFL(r_sMax, j);
+                            reduce_pixel_horizon(rw, bMin, bMax);
+                            const float jbfx = GSHFL(r_bfx, j), jbfy = GSHFL(r_bfy, j);
+                            const float jAx = GSHFL(r_uvAx, j), jAy = GSHFL(r_uvAy, j);
+                            const float jBx = GSHFL(r_uvBx, j), jBy = GSHFL(r_uvBy, j);
+                            const int jLen = GSHFL(r_len, j), jCi = GSHFL(r_ci, j);
+                            for (int y = bMin + gl; y <= bMax; y += G) { // :519-533
+                                if (!((rw.seen[y >> 5] >> (y & 31)) & 1u)) {
+                                    float l = unlerpf(jbfx, jbfy, (float)y);
+                                    float wx = lerpf(jAx, jBx, l), wy = lerpf(jAy, jBy, l);
+                                    float u = wy / wx;
+                                    int idx = max(0, min(jLen - 1, f2i(floorf(u)))) + jCi;
+                                    row[y] = __ldg(colColors + idx);
+                                }
+                            }
+                            __syncwarp(gmask);
+                            for (int w = (bMin >> 5) + gl; w <= (bMax >> 5); w += G) {
+                                uint32_t m = FULL_MASK;
+                                if (w == (bMin >> 5)) m &= mask_from(bMin);
+                                if (w == (bMax >> 5)) m &= mask_to(bMax);
+                                const uint32_t old = rw.seen[w];
+                                if (COUNTERS) acc.px_voxel += __popc(~old & m);
+                                rw.seen[w] = old | m;
+                            }
+                            __syncwarp(gmask);
+                            frustumDirMaxWorld = EPS; // a pixel was written (:522)
+                            if (rw.nf_min > rw.nf_max) { terminated = true; visitedHere = j + 1 - base; break; } // :535-539
+                        }
+                        // cap of run j :581-609, re-tested against the state the side span left behind
+                        const bool wCapNow = capOk && span_would_write(rw, r_cMin, r_cMax);
+                        if (GSHFL((int)wCapNow, j)) {
+                            int bMin = GSHFL(r_cMin, j), bMax = GSHFL(r_cMax, j);
+                            reduce_pixel_horizon(rw, bMin, bMax);
+                            const uint32_t color = __ldg(colColors + GSHFL(r_capIdx, j));
+                            for (int y = bMin + gl; y <= bMax; y += G) // :595-602
+                                if (!((rw.seen[y >> 5] >> (y & 31)) & 1u)) row[y] = color;
+                            __syncwarp(gmask);
+                            for (int w = (bMin >> 5) + gl; w <= (bMax >> 5); w += G) {
+                                uint32_t m = FULL_MASK;
+                                if (w == (bMin >> 5)) m &= mask_from(bMin);
+                                if (w == (bMax >> 5)) m &= mask_to(bMax);
+                                const uint32_t old = rw.seen[w];
+                                if (COUNTERS) acc.px_voxel += __popc(~old & m);
+                                rw.seen[w] = old | m;
+                            }
+                            __syncwarp(gmask);
+                            frustumDirMaxWorld = EPS; // :598
+                            if (rw.nf_min > rw.nf_max) { terminated = true; visitedHere = j + 1 - base; break; } // :604-608
+                        }
+                    }
+                    if (COUNTERS && gl == 0) acc.runs_visited += visitedHere;
+                    STAMP(4);
+                } else {
+                // ================= columns with more than G runs: G runs per pass ==========================================
+                STAMP(4);
+                roundCols = 0u; // the pass below reuses nothing of the cache and the cache is not valid for this column
                 int chunkStartY = ITER > 0 ? world.dim_y : 0;                 // running elementBounds, exact in int
                 bool colStop = false;
                 for (int k0 = 0; k0 < runCount && !colStop && !terminated; k0 += G) {
@@ -536,6 +732,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                     if (breakMask) { nVisit = __ffs(breakMask); colStop = true; } // the breaking run itself was dereferenced
                     const bool active = solid && gl < nVisit && !above && !below;
 
+                    STAMP(5);
                     // ---- per-lane span geometry; depends only on column constants ------------------------------
                     bool sideOk = false, capOk = false;
                     int sMin = 0, sMax = 0, cMin = 0, cMax = 0, capIdx = 0;
@@ -571,6 +768,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                         }
                     }
 
+                    STAMP(6);
                     // ---- commit, in reference order, only the spans that still hold an unwritten pixel ----------
                     uint32_t pending = GBALLOT(sideOk || capOk);
                     int visitedHere = nVisit;
@@ -633,12 +831,15 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                         }
                     }
                     if (COUNTERS && gl == 0) acc.runs_visited += visitedHere;
+                    STAMP(4);
+                }
                 }
                 if (terminated) { cellsDone = c + 1; break; }
             }
             if (COUNTERS && gl == 0) acc.dda_steps += cellsDone;
             if (endKind != 0) reachedEnd = true;
         }
+        STAMP(7);
         // WriteSkybox :699-708 — :248,268,323,401,419,537,606,619 all end here
         __syncwarp(gmask);
         for (int y = rw.orig_min + gl; y <= rw.orig_max; y += G)
@@ -653,6 +854,10 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
         }
     }
 
+    STAMP(0);
+    if (TIMING && f.timing && gl == 0)
+        for (int i = 0; i < CVXD_TIMING_REGIONS; i++) f.timing[(int64_t)flat * CVXD_TIMING_REGIONS + i] = tAcc[i];
+#undef STAMP
     if (COUNTERS && f.counters) {
         if (acc.dda_steps) atomicAdd(&f.counters->dda_steps, acc.dda_steps);
         if (acc.columns_nonempty) atomicAdd(&f.counters->columns_nonempty, acc.columns_nonempty);
@@ -751,9 +956,13 @@ static cudaError_t launch_phase1_g(const cvxd_world& world, const cvxd_frame& fr
     constexpr int groupsPerCta = CVXD_THREADS_PER_CTA / G;
     const int blocks = (n + groupsPerCta - 1) / groupsPerCta;
     const int seenWords = ((frame.width > frame.height ? frame.width : frame.height) + 31) >> 5;
-    const size_t smem = (size_t)groupsPerCta * seenWords * sizeof(uint32_t);
-    if (frame.counters) phase1_kernel<G, true><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
-    else                phase1_kernel<G, false><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
+    const size_t smem = (size_t)groupsPerCta * (seenWords + G) * sizeof(uint32_t);
+    if (frame.timing) {
+        if (G == 32) phase1_kernel<32, false, true><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
+        else return cudaErrorInvalidValue; // the timing build exists for the default group width only
+    }
+    else if (frame.counters) phase1_kernel<G, true, false><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
+    else                     phase1_kernel<G, false, false><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
     return cudaGetLastError();
 }
 

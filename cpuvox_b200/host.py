@@ -303,6 +303,13 @@ class RenderManager:
         self._ck(lib.cvx_debug_ray_setup(self._ctx, C.byref(setup), out, total))
         return np.frombuffer(out, dtype=RAY_STATE_DTYPE, count=total).copy()
 
+    def ray_timing(self, setup: FrameSetup) -> np.ndarray:
+        """Debug: cycles per code region per ray, shape (rays, 8) — see cvx_debug_ray_timing."""
+        total = sum(max(0, setup.segments[k].ray_count) for k in range(4))
+        out = np.zeros((max(1, total), 8), dtype=np.int64)
+        self._ck(lib.cvx_debug_ray_timing(self._ctx, C.byref(setup), _ptr(out), total))
+        return out[:total]
+
     def device_frame_ptr(self) -> Tuple[int, int]:
         p, n = C.c_void_p(), C.c_int64()
         self._ck(lib.cvx_device_frame(self._ctx, C.byref(p), C.byref(n)))

@@ -137,6 +137,7 @@ SYMBOLS = {
     "cvx_ipc_open": (C.c_int, [_P, C.POINTER(C.c_uint8 * 64), C.POINTER(_P)]),
     "cvx_ipc_close": (C.c_int, [_P, _P]),
     "cvx_debug_ray_setup": (C.c_int, [_P, C.POINTER(FrameSetup), C.POINTER(RayState), _I32]),
+    "cvx_debug_ray_timing": (C.c_int, [_P, C.POINTER(FrameSetup), _P, _I32]),
     "cvx_host_quat_euler": (None, [_F, _F, _F, C.POINTER(_F * 4)]),
     "cvx_host_limit_rotation_horizon": (None, [C.POINTER(Pose)]),
     "cvx_host_setup_lods": (None, [_I32, _I32, _I32, _F, _F, C.POINTER(_F * LOD_LEVELS)]),

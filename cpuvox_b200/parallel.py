@@ -101,6 +101,7 @@ class ShardedRenderManager:
         self.device, self.rank, self.world_size, self.gather, self.group = device, rank, world_size, gather, group
         self._root_frame_ptr = 0      # mapped pointer to rank 0's framebuffer (p2p, rank != 0)
         self._frame_tensor = None     # torch int32 tensor aliasing this rank's framebuffer (reduce)
+        self._stream = None
 
     def upload_world(self, world: World):
         self.rm.upload_world(world)
@@ -124,7 +125,10 @@ class ShardedRenderManager:
         else:
             # render into a torch-owned buffer on torch's stream so NCCL sees the same memory and ordering
             self._frame_tensor = torch.zeros(width * height, dtype=torch.int32, device=f"cuda:{self.device}")
-            self.rm.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+            if self._stream is None:  # an explicit stream: torch's default stream is the NULL handle (= "own stream" for cvx_set_stream)
+                self._stream = torch.cuda.Stream(self.device)
+            torch.cuda.set_stream(self._stream)
+            self.rm.set_stream(self._stream.cuda_stream)
             self.rm.set_external_frame(self._frame_tensor.data_ptr())
 
     def draw_world_sharded(self, pose: CameraPose, weights: Optional[Sequence[float]] = None) -> FrameSetup:

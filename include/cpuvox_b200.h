@@ -91,7 +91,8 @@ int cvx_destroy(cvx_ctx* ctx);
 /* Error text of the last failing call on this context (or of cvx_create when ctx == NULL). */
 const char* cvx_last_error(const cvx_ctx* ctx);
 
-/* Optional: run on a caller-owned CUDA stream (cudaStream_t) instead of the context's own. */
+/* Optional: run on a caller-owned CUDA stream (cudaStream_t) instead of the context's own. NULL restores the
+ * context's own stream; to use the legacy default stream pass cudaStreamLegacy. */
 int cvx_set_stream(cvx_ctx* ctx, void* cuda_stream);
 
 /* ---- world hand-off: World / WorldAllocator, Assets/Code/World.cs:8-43,261-313 ------------
@@ -185,6 +186,11 @@ typedef struct cvx_ray_state {
     float intersection_distances[2];
 } cvx_ray_state;
 int cvx_debug_ray_setup(cvx_ctx* ctx, const cvx_frame_setup* setup, cvx_ray_state* out, int32_t max_rays);
+/* Debug: run Phase 1 once with per-ray cycle counters; CVX_TIMING_REGIONS int64 per flat ray index:
+ * 0 setup/other, 1 DDA look-ahead + header fetch, 2 column selection (frustum cull), 3 frustum re-narrowing,
+ * 4 run fetch + bounds, 5 span geometry, 6 span commit, 7 skybox fill. Returns the frame's ray count. */
+#define CVX_TIMING_REGIONS 8
+int cvx_debug_ray_timing(cvx_ctx* ctx, const cvx_frame_setup* setup, int64_t* out_cycles, int32_t max_rays);
 
 /* =============================================================================================
  * Host-side helpers (pure CPU, no device): C++ restatement of the managed code around the path,
