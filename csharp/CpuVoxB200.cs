@@ -1,0 +1,102 @@
+// CpuVoxB200.cs — P/Invoke binding of libcpuvox_b200.so (include/cpuvox_b200.h) for the reference's C# host.
+// NOT compiled or run in the build environment (no dotnet/mono/csc in the image); it is the stub a maintainer of
+// pipliz/cpuvox adds next to Assets/Code/RenderManager.cs. Struct layouts mirror the header field for field; the
+// managed types they shadow are cited on each declaration.
+using System;
+using System.Runtime.InteropServices;
+
+public static unsafe class CpuVoxB200
+{
+	const string LIB = "cpuvox_b200"; // libcpuvox_b200.so / cpuvox_b200.dll on the loader path
+
+	public const int LOD_LEVELS = 6; // UnityManager.LOD_LEVELS, Assets/Code/UnityManager.cs:42
+
+	[StructLayout(LayoutKind.Sequential)]
+	public struct Segment // RenderManager.SegmentData, Assets/Code/RenderManager.cs:503-510 — identical layout, can be blitted
+	{
+		public float MinScreenX, MinScreenY;
+		public float MaxScreenX, MaxScreenY;
+		public float CamLocalPlaneRayMinX, CamLocalPlaneRayMinY;
+		public float CamLocalPlaneRayMaxX, CamLocalPlaneRayMaxY;
+		public int RayCount;
+	}
+
+	[StructLayout(LayoutKind.Sequential)]
+	public struct Camera // CameraData, Assets/Code/Utils/CameraData.cs:11-36
+	{
+		public fixed float WorldToScreen[16]; // float4x4 stored c0, c1, c2, c3 (Unity.Mathematics column order)
+		public float PositionX, PositionZ;
+		public float PositionY;
+		public int InverseElementIterationDirection;
+		public float FarClip;
+		public fixed float LODDistances[LOD_LEVELS];
+	}
+
+	[StructLayout(LayoutKind.Sequential)]
+	public struct FrameSetup
+	{
+		public Segment Segment0, Segment1, Segment2, Segment3;
+		public Camera Camera;
+		public float VanishingPointX, VanishingPointY;
+	}
+
+	[StructLayout(LayoutKind.Sequential)]
+	public struct Counters
+	{
+		public ulong DdaSteps, ColumnsNonEmpty, RunsVisited, PxVoxel, PxSky, Rays;
+	}
+
+	[StructLayout(LayoutKind.Sequential)]
+	public struct Config { public int Device; public int Flags; }
+
+	[DllImport(LIB)] public static extern int cvx_create(ref Config config, out IntPtr ctx);
+	[DllImport(LIB)] public static extern int cvx_destroy(IntPtr ctx);
+	[DllImport(LIB)] public static extern IntPtr cvx_last_error(IntPtr ctx);
+	[DllImport(LIB)] public static extern int cvx_world_upload(IntPtr ctx, int lod, int dimX, int dimY, int dimZ, void* blob, long bytes, int columnCount);
+	[DllImport(LIB)] public static extern int cvx_world_free(IntPtr ctx);
+	[DllImport(LIB)] public static extern int cvx_set_resolution(IntPtr ctx, int width, int height);
+	[DllImport(LIB)] public static extern int cvx_draw(IntPtr ctx, ref FrameSetup setup);
+	[DllImport(LIB)] public static extern int cvx_draw_batch(IntPtr ctx, FrameSetup* setups, int nViews, void* dstFrames);
+	[DllImport(LIB)] public static extern int cvx_sync(IntPtr ctx);
+	[DllImport(LIB)] public static extern int cvx_read_frame(IntPtr ctx, void* dstArgb, long bytes);
+	[DllImport(LIB)] public static extern int cvx_read_raybuffer(IntPtr ctx, int which, void* dstArgb, long bytes);
+	[DllImport(LIB)] public static extern int cvx_get_counters(IntPtr ctx, out Counters counters, int reset);
+	[DllImport(LIB)] public static extern int cvx_device_frame(IntPtr ctx, out IntPtr devicePtr, out long bytes);
+
+	public static void Check (int code, IntPtr ctx)
+	{
+		if (code < 0) {
+			throw new InvalidOperationException("cpuvox_b200 error " + code + ": " + Marshal.PtrToStringAnsi(cvx_last_error(ctx)));
+		}
+	}
+
+	/// <summary>World hand-off: WorldAllocator.GetStartPointer/GetByteLength (Assets/Code/World.cs:273-283), once per LOD.</summary>
+	public static void UploadWorlds (IntPtr ctx, World[] worldLODs)
+	{
+		for (int lod = 0; lod < worldLODs.Length; lod++) {
+			if (!worldLODs[lod].Exists) { continue; }
+			int3 d = worldLODs[lod].Dimensions;
+			Check(cvx_world_upload(ctx, lod, d.x << lod, d.y << lod, d.z << lod, // LOD-0 dimensions
+				worldLODs[lod].Storage.GetStartPointer(), worldLODs[lod].Storage.GetByteLength(), worldLODs[lod].ColumnCount), ctx);
+		}
+	}
+
+	/// <summary>Replaces the body of RenderManager.DrawSegments + ApplyPartials + BlitSegments (RenderManager.cs:156-189).</summary>
+	public static void Draw (IntPtr ctx, Unity.Collections.NativeArray<RenderManager.SegmentData> segments, ref CameraData camData, Unity.Mathematics.float2 vanishingPointScreenSpace)
+	{
+		FrameSetup s = default;
+		Segment* dst = &s.Segment0;
+		for (int i = 0; i < 4; i++) {
+			RenderManager.SegmentData sd = segments[i];
+			dst[i] = *(Segment*)&sd; // same sequential layout
+		}
+		fixed (CameraData* cam = &camData) {
+			// CameraData = float4x4 + float2 + float + bool(4-byte marshalled) + float + fixed float[6]; copy field-wise if the
+			// managed bool is 1 byte in your build.
+			Buffer.MemoryCopy(cam, &s.Camera, sizeof(Camera), sizeof(Camera));
+		}
+		s.VanishingPointX = vanishingPointScreenSpace.x;
+		s.VanishingPointY = vanishingPointScreenSpace.y;
+		Check(cvx_draw(ctx, ref s), ctx);
+	}
+}
