@@ -22,6 +22,7 @@
  *    bit for bit.
  */
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 #include "device_types.h"
 
@@ -39,7 +40,7 @@ __device__ __forceinline__ float signf(float x) { return (float)((x > 0.0f ? 1 :
 __device__ __forceinline__ float minf_(float a, float b) { return a < b ? a : b; }
 __device__ __forceinline__ float maxf_(float a, float b) { return a > b ? a : b; }
 // (int)float as x64 cvttss2si: NaN / out of range -> INT_MIN
-__device__ __forceinline__ int f2i(float f) { return (f >= -2147483648.0f && f < 2147483648.0f) ? (int)f : (int)0x80000000; }
+__device__ __forceinline__ int f2i(float f) { const int r = __float2int_rz(f); return f < 2147483648.0f ? r : (int)0x80000000; } // cvt saturates low; NaN/high -> INT_MIN
 __device__ __forceinline__ float float_epsilon() { return __int_as_float(1); }
 
 // ---- SegmentDDAData (Assets/Code/Utils/SegmentDDAData.cs) -------------------------------------------------
@@ -72,15 +73,6 @@ __device__ __forceinline__ void dda_next_lod(Dda& d, int voxelSize) { // :31-73
     d.px -= rx; d.pz -= rz;
     d.tdx *= 2.0f; d.tdz *= 2.0f;
     d.sx *= 2; d.sz *= 2;
-}
-
-__device__ __forceinline__ bool dda_step(Dda& d, float farClip) { // :135-150
-    float crossed;
-    if (d.tmx < d.tmz) { crossed = d.tmx; d.tmx += d.tdx; d.px += d.sx; }
-    else               { crossed = d.tmz; d.tmz += d.tdz; d.pz += d.sz; }
-    d.dl = crossed;
-    d.dn = minf_(d.tmx, d.tmz);
-    return crossed >= farClip;
 }
 
 __device__ bool dda_step_to_world(Dda& d, float dimX, float dimZ) { // StepToWorldIntersection :75-130
@@ -224,40 +216,84 @@ __device__ void setup_ray(const cvxd_world& world, const cvxd_frame& f, int flat
 }
 
 // ---- written-pixel bitmask helpers -------------------------------------------------------------------------
-// first index >= start whose bit is clear, at most limit+1  ("while (i <= limit && seen[i]) i++")
-__device__ __forceinline__ int scan_up(const uint32_t* seen, int start, int limit) {
-    int i = start;
-    while (i <= limit) {
-        uint32_t w = ~seen[i >> 5] & (FULL_MASK << (i & 31));
-        if (w) { int j = (i & ~31) + __ffs(w) - 1; return j <= limit ? j : limit + 1; }
-        i = (i & ~31) + 32;
-    }
-    return limit + 1 > start ? limit + 1 : start;
-}
-// last index <= start whose bit is clear, at least limit-1  ("while (i >= limit && seen[i]) i--")
-__device__ __forceinline__ int scan_down(const uint32_t* seen, int start, int limit) {
-    int i = start;
-    while (i >= limit) {
-        uint32_t w = ~seen[i >> 5] & (FULL_MASK >> (31 - (i & 31)));
-        if (w) { int j = (i & ~31) + 31 - __clz(w); return j >= limit ? j : limit - 1; }
-        i = (i & ~31) - 1;
-    }
-    return limit - 1 < start ? limit - 1 : start;
-}
+// Two levels in shared memory: seen[w] has one bit per pixel of the row, full[w >> 5] has bit (w & 31) set when seen[w] is
+// all ones. Scans and range tests hop over fully written stretches through the second level (at most 8 words at 8K).
 // bits [a & 31 .. 31] of the word holding a, and bits [0 .. b & 31] of the word holding b
 __device__ __forceinline__ uint32_t mask_from(int a) { return FULL_MASK << (a & 31); }
 __device__ __forceinline__ uint32_t mask_to(int b) { return FULL_MASK >> (31 - (b & 31)); }
+
+// index of the first word in [wlo, whi] that is not fully written, or whi + 1
+__device__ __forceinline__ int next_open_word(const uint32_t* full, int wlo, int whi) {
+    int w = wlo;
+    while (w <= whi) {
+        const uint32_t m = ~full[w >> 5] & mask_from(w);
+        if (m) { const int r = (w & ~31) + __ffs(m) - 1; return r <= whi ? r : whi + 1; }
+        w = (w & ~31) + 32;
+    }
+    return whi + 1;
+}
+// index of the last word in [wlo, whi] that is not fully written, or wlo - 1
+__device__ __forceinline__ int prev_open_word(const uint32_t* full, int wlo, int whi) {
+    int w = whi;
+    while (w >= wlo) {
+        const uint32_t m = ~full[w >> 5] & mask_to(w);
+        if (m) { const int r = (w & ~31) + 31 - __clz(m); return r >= wlo ? r : wlo - 1; }
+        w = (w & ~31) - 1;
+    }
+    return wlo - 1;
+}
+// first index >= start whose bit is clear, at most limit+1  ("while (i <= limit && seen[i]) i++")
+__device__ __forceinline__ int scan_up(const uint32_t* seen, const uint32_t* full, int start, int limit) {
+    if (start > limit) return start;
+    uint32_t x = ~seen[start >> 5] & mask_from(start);
+    int w = start >> 5;
+    if (!x) {
+        w = next_open_word(full, w + 1, limit >> 5);
+        if (w > (limit >> 5)) return limit + 1;
+        x = ~seen[w];
+    }
+    const int j = (w << 5) + __ffs(x) - 1;
+    return j <= limit ? j : limit + 1;
+}
+// last index <= start whose bit is clear, at least limit-1  ("while (i >= limit && seen[i]) i--")
+__device__ __forceinline__ int scan_down(const uint32_t* seen, const uint32_t* full, int start, int limit) {
+    if (start < limit) return start;
+    uint32_t x = ~seen[start >> 5] & mask_to(start);
+    int w = start >> 5;
+    if (!x) {
+        w = prev_open_word(full, limit >> 5, w - 1);
+        if (w < (limit >> 5)) return limit - 1;
+        x = ~seen[w];
+    }
+    const int j = (w << 5) + 31 - __clz(x);
+    return j >= limit ? j : limit - 1;
+}
 // any clear bit in [a, b] (a <= b, both inside the row)
-__device__ __forceinline__ bool any_unseen(const uint32_t* seen, int a, int b) {
+__device__ __forceinline__ bool any_unseen(const uint32_t* seen, const uint32_t* full, int a, int b) {
     const int wa = a >> 5, wb = b >> 5;
     if (wa == wb) return (~seen[wa] & mask_from(a) & mask_to(b)) != 0u;
-    if (~seen[wa] & mask_from(a)) return true;
-    for (int w = wa + 1; w < wb; w++) if (~seen[w]) return true;
-    return (~seen[wb] & mask_to(b)) != 0u;
+    if ((~seen[wa] & mask_from(a)) | (~seen[wb] & mask_to(b))) return true;
+    return wa + 1 < wb && next_open_word(full, wa + 1, wb - 1) < wb;
+}
+// mark [a, b] written: lane `gl` of G handles every G-th word; returns how many of them were new (for the counters)
+template <int G>
+__device__ __forceinline__ int mark_seen(uint32_t* seen, uint32_t* full, int a, int b, int gl) {
+    int fresh = 0;
+    for (int w = (a >> 5) + gl; w <= (b >> 5); w += G) {
+        uint32_t m = FULL_MASK;
+        if (w == (a >> 5)) m &= mask_from(a);
+        if (w == (b >> 5)) m &= mask_to(b);
+        const uint32_t old = seen[w], now = old | m;
+        fresh += __popc(~old & m);
+        seen[w] = now;
+        if (now == FULL_MASK && old != FULL_MASK) atomicOr(&full[w >> 5], 1u << (w & 31));
+    }
+    return fresh;
 }
 
 struct RowState {
     uint32_t* seen;         // shared-memory bitmask of this row
+    uint32_t* full;         // second level: one bit per word of `seen` that is all ones
     uint32_t* row;          // raybuffer row
     int orig_min, orig_max; // originalNextFreePixelMin/Max
     int nf_min, nf_max;     // nextFreePixelMin/Max
@@ -271,7 +307,7 @@ struct RowState {
 __device__ __forceinline__ bool span_would_write(const RowState& rw, int bMin, int bMax) {
     if (!(bMax >= rw.nf_min && bMin <= rw.nf_max)) return false;
     const int a = bMin > rw.nf_min ? bMin : rw.nf_min, b = bMax < rw.nf_max ? bMax : rw.nf_max;
-    return a <= b && any_unseen(rw.seen, a, b);
+    return a <= b && any_unseen(rw.seen, rw.full, a, b);
 }
 
 // ReducePixelHorizon :660-697 (uniform across the group)
@@ -279,14 +315,14 @@ __device__ __forceinline__ void reduce_pixel_horizon(RowState& rw, int& bMin, in
     if (bMin <= rw.nf_min) {
         bMin = rw.nf_min;
         if (bMax >= rw.nf_min) {
-            rw.nf_min = scan_up(rw.seen, bMax + 1, rw.orig_max);
+            rw.nf_min = scan_up(rw.seen, rw.full, bMax + 1, rw.orig_max);
             rw.fb_min = rw.nf_min - 0.501f;
         }
     }
     if (bMax >= rw.nf_max) {
         bMax = rw.nf_max;
         if (bMin <= rw.nf_max) {
-            rw.nf_max = scan_down(rw.seen, bMin - 1, rw.orig_min);
+            rw.nf_max = scan_down(rw.seen, rw.full, bMin - 1, rw.orig_min);
             rw.fb_max = rw.nf_max + 0.501f;
         }
     }
@@ -305,6 +341,12 @@ __device__ __forceinline__ void touch(const uint32_t* p) {
  * Neighbouring rows (adjacent rays of one segment) share a warp: they walk nearly the same columns, so the groups of
  * a warp stay mostly convergent while the number of rays in flight per SM grows by 32/G.
  */
+#ifndef CVXD_HULL
+#define CVXD_HULL 1
+#endif
+#ifndef CVXD_MULTI_COL
+#define CVXD_MULTI_COL 1
+#endif
 #ifndef CVXD_MIN_CTAS_PER_SM
 #define CVXD_MIN_CTAS_PER_SM 4
 #endif
@@ -341,8 +383,11 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
     Acc acc = {0, 0, 0, 0, 0}; // per lane; summed with atomics at the end (COUNTERS only)
     if (COUNTERS && gl == 0) acc.dda_steps = (unsigned long long)rs.lod_steps;
     RowState rw;
-    rw.seen = seen_all + group * (seenWords + G);
-    int* scratch = (int*)(rw.seen + seenWords); // G ints: lane of a round -> batch cell of its column
+    const int fullWords = (seenWords + 31) >> 5;
+    rw.seen = seen_all + group * (seenWords + fullWords + 9 * G);
+    rw.full = rw.seen + seenWords;
+    int* scratch = (int*)(rw.full + fullWords); // G ints: lane of a round -> batch cell of its column
+    uint32_t* cache = (uint32_t*)(scratch + G); // 8 x G words: commit-only fields of the round cache
     rw.row = row;
     rw.orig_min = sg.pix_min; rw.orig_max = sg.pix_max;
     rw.nf_min = rw.orig_min; rw.nf_max = rw.orig_max;
@@ -352,7 +397,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
         for (int y = rw.orig_min + gl; y <= rw.orig_max; y += G) row[y] = SKYBOX_ARGB;
         if (COUNTERS && gl == 0 && rw.orig_max >= rw.orig_min) acc.px_sky += rw.orig_max - rw.orig_min + 1;
     } else {
-        for (int w = gl; w < ((rowLen + 31) >> 5); w += G) rw.seen[w] = 0u; // stackalloc, zero-initialised (:208)
+        for (int w = gl; w < seenWords + fullWords; w += G) rw.seen[w] = 0u; // stackalloc, zero-initialised (:208); both levels
         __syncwarp(gmask);
 
         Dda ray = rs.dda;
@@ -381,26 +426,69 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
         }
         const int maskX = world.dim_x - 1, maskZ = world.dim_z - 1;
 
+        // Side-span pixels are a colour gather followed by a store: the store is deferred until this lane's next gather (or the end
+        // of the ray), so the gather's latency is not on the ray's critical path. Nothing in this kernel reads the row back.
+        int pendY = -1; uint32_t pendColor = 0u;
         bool terminated = false; // ray ended inside the loop: skybox the rest and stop
         bool reachedEnd = false; // far clip or world exit
         while (!terminated && !reachedEnd) {
             STAMP(1);
-            // ---- look ahead: up to G cells of the DDA, lane i of the group keeps cell i -------------------------
-            int n = 0, endKind = 0; // 1 = next cell is outside the world, 2 = far clip crossed after the last cell
-            int myLod = 0, myIdx = 0; float myDl = 0.0f, myDn = 0.0f;
-            for (int i = 0; i < G; i++) {
-                if (ray.dl >= lodMax) { // :237-243
-                    dda_next_lod(ray, voxelScale);
-                    lod++; voxelScale *= 2;
-                    lodMax = f.lod_dist[lod];
+            // ---- look ahead: the next G cells of the DDA at once, lane k of the group gets cell k -------------------------
+            // Step() (SegmentDDAData.cs:135-150) crosses the x boundary when tMax.x < tMax.y, else the z boundary, and then adds
+            // tDelta to that tMax: the crossing times are the merge of the two sequences X[a] = tMax.x + a additions of tDelta.x and
+            // Z[b] likewise (ties go to z). The two chains are accumulated serially (same float additions as the reference), lane j
+            // keeps X[j] and Z[j]; lane k then finds by a merge-path binary search how many of its first k steps were x steps —
+            // a_k = the largest a with X[a-1] < Z[k-a] — which gives its cell, its last/next distances and its header address.
+            if (ray.dl >= lodMax) { // :237-243, tested once per visited cell: here for cell 0, for later cells by cutting the batch
+                dda_next_lod(ray, voxelScale);
+                lod++; voxelScale *= 2;
+                lodMax = f.lod_dist[lod];
+            }
+            float myX = ray.tmx, myZ = ray.tmz, xEnd, zEnd;
+            {
+                float x = ray.tmx, z = ray.tmz;
+#pragma unroll
+                for (int j = 1; j < G; j++) {
+                    x += ray.tdx; z += ray.tdz;
+                    if (gl == j) { myX = x; myZ = z; }
                 }
-                if (((ray.px & maskX) != ray.px) || ((ray.pz & maskZ) != ray.pz)) { endKind = 1; break; } // World.cs:135-138
-                if (gl == i) {
-                    myLod = lod; myDl = ray.dl; myDn = ray.dn;
-                    myIdx = (ray.px >> lod) * world.lods[lod].mul_x + (ray.pz >> lod); // GetIndexKnownInBounds World.cs:145-149
+                xEnd = x + ray.tdx; zEnd = z + ray.tdz; // X[G], Z[G]
+            }
+            int aK = 0;
+            {
+                int lo = 0, hi = gl;
+#pragma unroll
+                for (int it = 0; it < (G == 32 ? 5 : (G == 16 ? 4 : 3)); it++) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    const float xv = GSHFL(myX, mid > 0 ? mid - 1 : 0), zv = GSHFL(myZ, gl - mid >= 0 ? gl - mid : 0);
+                    if (lo < hi) { if (xv < zv) lo = mid; else hi = mid - 1; }
                 }
-                n = i + 1;
-                if (dda_step(ray, farClip)) { endKind = 2; break; }
+                aK = lo;
+            }
+            const int bK = gl - aK;
+            const float xa = GSHFL(myX, aK), zb = GSHFL(myZ, bK); // tMax of my cell
+            const bool xStep = xa < zb;                          // which boundary Step() crosses leaving my cell
+            const float myDn = xStep ? xa : zb;                  // crossed distance = next intersection of my cell
+            float myDl = __shfl_up_sync(gmask, myDn, 1, G);      // the previous cell's crossing is my last intersection
+            if (gl == 0) myDl = ray.dl;
+            const int cellX = ray.px + aK * ray.sx, cellZ = ray.pz + bK * ray.sz;
+            const bool oob = ((cellX & maskX) != cellX) || ((cellZ & maskZ) != cellZ);   // World.cs:135-138
+            // first event in walk order: LOD switch before cell k (k >= 1), world exit at cell k, far clip after cell k (:613-615)
+            const uint32_t swMask = GBALLOT(gl >= 1 && myDl >= lodMax), oobMask = GBALLOT(oob), farMask = GBALLOT(myDn >= farClip);
+            const int kS = swMask ? __ffs(swMask) - 1 : G, kO = oobMask ? __ffs(oobMask) - 1 : G, kF = farMask ? __ffs(farMask) - 1 : G;
+            int n, endKind = 0; // 1 = next cell is outside the world, 2 = far clip crossed after the last cell
+            if (kS <= kO && kS <= kF) n = kS;                    // cut: the next batch starts with the LOD switch (or n == G: plain end of batch)
+            else if (kO <= kF) { n = kO; endKind = 1; }
+            else { n = kF + 1; endKind = 2; }
+            const int myIdx = (cellX >> lod) * world.lods[lod].mul_x + (cellZ >> lod); // GetIndexKnownInBounds World.cs:145-149
+            const int myLod = lod;                               // one LOD per batch
+            if (endKind == 0 && n > 0) {                         // advance the ray to the cell after the batch
+                const int aN = GSHFL(aK + (xStep ? 1 : 0), n - 1), bN = n - aN;
+                const float tx = GSHFL(myX, aN < G ? aN : 0), tz = GSHFL(myZ, bN < G ? bN : 0);
+                ray.tmx = aN < G ? tx : xEnd; ray.tmz = bN < G ? tz : zEnd;
+                ray.px += aN * ray.sx; ray.pz += bN * ray.sz;
+                ray.dl = GSHFL(myDn, n - 1);
+                ray.dn = minf_(ray.tmx, ray.tmz);
             }
             uint4 hdr = make_uint4(0, 0, 0, 0);
             if (gl < n) hdr = __ldg(world.lods[myLod].headers + myIdx);
@@ -416,10 +504,34 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
             uint32_t roundInvalid = 0u;   // lanes holding an invalid element (Length == 0), which ends its column (:445-447)
             int myBase = 0;               // batch lane c: first round lane of column c
             // per-lane cached run: element fields, world-Y bounds, side span and cap span (none of it depends on the written-pixel state)
-            int r_ci = 0, r_len = 0, r_sMin = 0, r_sMax = 0, r_cMin = 0, r_cMax = 0, r_capIdx = 0, r_capKind = 0;
+            // (what only the commit of a span needs — colour indices, unrounded bounds, 1/w and u/w of both ends — is parked in
+            // shared memory, cache[field * G + lane], and read back by the whole group at the committing lane's index)
+            int r_ci = 0, r_sMin = 0, r_sMax = 0, r_cMin = 0, r_cMax = 0, r_capKind = 0;
             bool r_sideClip = false, r_capClip = false;
-            float r_eMin = 0.0f, r_eMax = 0.0f, r_bfx = 0.0f, r_bfy = 0.0f, r_uvAx = 0.0f, r_uvAy = 0.0f, r_uvBx = 0.0f, r_uvBy = 0.0f;
+            float r_eMin = 0.0f, r_eMax = 0.0f;
             const int myRunCount = (int)(hdr.y & 0xffffu);
+
+            // Product builds (no counters): screen-axis hull of this lane's column — the projections of its solid extent
+            // [worldMin, worldMax] on the last and next line. Every side span lies between two points of the last line and every cap
+            // span between a last-line and a next-line point of one height (:478-481,554-562), and with all four corners in front of
+            // the near plane the projection is monotone along those lines, so all spans of the column lie inside the hull (+-1 pixel
+            // for rounding). While the frustum is valid (not the float.Epsilon sentinel) a column is entered without side effects unless
+            // one of its spans holds an unwritten pixel (see span_would_write), so a column whose hull holds none is skipped exactly
+            // like a culled one. Counter builds enter every column the reference enters, to count its runs.
+            int hullMin = INT_MIN / 2, hullMax = INT_MAX / 2; // "cannot tell": never skipped
+            if (CVXD_HULL && !COUNTERS && myNonEmpty) {
+                const float pLo = unlerpf(0.0f, worldMaxY, myWorldMin), pHi = unlerpf(0.0f, worldMaxY, myWorldMax);
+                const F3 bL = F3{planeBottom.x + planeDir.x * myDl, planeBottom.y + planeDir.y * myDl, planeBottom.z + planeDir.z * myDl};
+                const F3 tL = F3{planeTop.x + planeDir.x * myDl, planeTop.y + planeDir.y * myDl, planeTop.z + planeDir.z * myDl};
+                const F3 bN = F3{planeBottom.x + planeDir.x * myDn, planeBottom.y + planeDir.y * myDn, planeBottom.z + planeDir.z * myDn};
+                const F3 tN = F3{planeTop.x + planeDir.x * myDn, planeTop.y + planeDir.y * myDn, planeTop.z + planeDir.z * myDn};
+                const F3 q0 = lerp3(bL, tL, pLo), q1 = lerp3(bL, tL, pHi), q2 = lerp3(bN, tN, pLo), q3 = lerp3(bN, tN, pHi);
+                if (q0.y > 0.0f && q1.y > 0.0f && q2.y > 0.0f && q3.y > 0.0f) { // all in front of the near plane (z' > 0 <=> w > near)
+                    const float a0 = q0.x / q0.z, a1 = q1.x / q1.z, a2 = q2.x / q2.z, a3 = q3.x / q3.z;
+                    const float lo = fminf(fminf(a0, a1), fminf(a2, a3)), hi = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+                    if (lo > -1.0e6f && hi < 1.0e6f) { hullMin = (int)floorf(lo) - 1; hullMax = (int)ceilf(hi) + 1; } // NaN fails both tests
+                }
+            }
 
             while (remaining) {
                 STAMP(2);
@@ -433,7 +545,8 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                     const float newMin = camY + frustumDirMinWorld * distBot;
                     const bool outOfWorld = newMin > worldMaxY || newMax < 0.0f;      // frustum left the world: ray ends
                     const bool culled = myWorldMin > newMax || myWorldMax < newMin;   // column outside the writable world bounds
-                    const uint32_t cand = GBALLOT(myNonEmpty && (outOfWorld || !culled)) & remaining;
+                    const bool inert = CVXD_HULL && !COUNTERS && !culled && !span_would_write(rw, hullMin, hullMax); // cannot write: no side effects
+                    const uint32_t cand = GBALLOT(myNonEmpty && (outOfWorld || !(culled || inert))) & remaining;
                     if (!cand) {
                         if (COUNTERS && gl == 0) acc.columns_nonempty += __popc(remaining);
                         remaining = 0u;
@@ -457,18 +570,14 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                 const int runCount = GSHFL(myRunCount, c);
                 const int cScale = 1 << cLod;
 
-                // :289-293
-                const F3 minLast = F3{planeBottom.x + planeDir.x * distLast, planeBottom.y + planeDir.y * distLast, planeBottom.z + planeDir.z * distLast};
-                const F3 minNext = F3{planeBottom.x + planeDir.x * distNext, planeBottom.y + planeDir.y * distNext, planeBottom.z + planeDir.z * distNext};
-                const F3 maxLast = F3{planeTop.x + planeDir.x * distLast, planeTop.y + planeDir.y * distLast, planeTop.z + planeDir.z * distLast};
-                const F3 maxNext = F3{planeTop.x + planeDir.x * distNext, planeTop.y + planeDir.y * distNext, planeTop.z + planeDir.z * distNext};
-
                 if (distLast > 2.0f && frustumDirMaxWorld == EPS) { // re-narrow the frustum :295-422
                     STAMP(3);
                     // The four clip parameters (last/next line x min/max end) and their projections are independent:
                     // lane L&3 of the group computes one of them (same operations as CameraData.cs:50-121), then they are shared.
                     const int L = gl & 3;
-                    const F3 pMin = (L & 2) ? minNext : minLast, pMax = (L & 2) ? maxNext : maxLast;
+                    const float dLine = (L & 2) ? distNext : distLast; // :289-293 for this lane's line
+                    const F3 pMin = F3{planeBottom.x + planeDir.x * dLine, planeBottom.y + planeDir.y * dLine, planeBottom.z + planeDir.z * dLine};
+                    const F3 pMax = F3{planeTop.x + planeDir.x * dLine, planeTop.y + planeDir.y * dLine, planeTop.z + planeDir.z * dLine};
                     const bool A = pMin.x > pMin.z * rw.fb_max, B = pMax.x > pMax.z * rw.fb_max;
                     const bool C = pMin.x < pMin.z * rw.fb_min, D = pMax.x < pMax.z * rw.fb_min;
                     const bool clipped = (A && B) || (!A && !B && C && D);
@@ -521,23 +630,28 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                     const int writableMin = f2i(floorf(clippedMin));
                     const int writableMax = f2i(ceilf(clippedMax));
                     if (writableMax < rw.nf_min || writableMin > rw.nf_max) { terminated = true; cellsDone = c + 1; break; }
-                    if (writableMin > rw.nf_min) rw.nf_min = scan_up(rw.seen, writableMin, rw.orig_max);
-                    if (writableMax < rw.nf_max) rw.nf_max = scan_down(rw.seen, writableMax, rw.orig_min);
+                    if (writableMin > rw.nf_min) rw.nf_min = scan_up(rw.seen, rw.full, writableMin, rw.orig_max);
+                    if (writableMax < rw.nf_max) rw.nf_max = scan_down(rw.seen, rw.full, writableMax, rw.orig_min);
                     if (rw.nf_min > rw.nf_max) { terminated = true; cellsDone = c + 1; break; }
                 }
 
-                const uint32_t* colBase = world.lods[cLod].elements + hOff;   // ElementGuardStart World.cs:175-178
-                const uint32_t* colColors = colBase + runCount + 2;           // ColorPointer :185-188
+                const uint32_t* colColors = world.lods[cLod].elements + hOff + runCount + 2; // ColorPointer World.cs:185-188
 
-                if (runCount <= G) {
-                    // ================= round path: columns of at most G runs =================================================
+                // ---- runs of this column (:424-611). A column of at most G runs is resolved from the round cache in one pass; a
+                // taller one goes through the same code G runs at a time (k0 = first run of the pass, yDone = world-Y extent of the
+                // runs before it, in LOD voxels times the LOD scale).
+                const bool tall = runCount > G;
+                int k0 = 0, yDone = 0;
+                bool colStop = false;
+                do {
                     STAMP(4);
-                    if (!((roundCols >> c) & 1u)) {
-                        // ---- form a round: this column plus the following columns that are likely to be entered, as long as
-                        // their runs fit in the G lanes. One run per lane: fetch, world-Y bounds (segmented prefix sum), and
-                        // the projected side/cap spans — the float-heavy part — once for all of them.
-                        uint32_t follow = remaining;
-                        if (frustumDirMaxWorld != EPS) {
+                    const int runsHere = tall ? (runCount - k0 < G ? runCount - k0 : G) : runCount;
+                    if (tall || !((roundCols >> c) & 1u)) {
+                        // ---- form a round: this column (pass) plus, if it is not a tall one, the following columns that are likely
+                        // to be entered, as long as their runs fit in the G lanes. One run per lane: fetch, world-Y bounds (segmented
+                        // prefix sum), and the projected side/cap spans — the float-heavy part — once for all of them.
+                        uint32_t follow = (CVXD_MULTI_COL && !tall) ? remaining : 0u;
+                        if (follow && frustumDirMaxWorld != EPS) {
                             const float distTop = frustumDirMaxWorld > 0.0f ? myDn : myDl;
                             const float distBot = frustumDirMinWorld < 0.0f ? myDn : myDl;
                             const float newMax = camY + frustumDirMaxWorld * distTop;
@@ -545,7 +659,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                             follow &= GBALLOT(myNonEmpty && !(myWorldMin > newMax || myWorldMax < newMin));
                         }
                         const uint32_t consider = (1u << c) | follow;
-                        const int v = ((consider >> gl) & 1u) ? myRunCount : 0;
+                        const int v = gl == c ? runsHere : (((consider >> gl) & 1u) ? myRunCount : 0);
                         int incl = v;
 #pragma unroll
                         for (int o = 1; o < G; o <<= 1) { int t = __shfl_up_sync(gmask, incl, o, G); if (gl >= o) incl += t; }
@@ -559,286 +673,149 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                         const int myStart = 31 - __clz(startMask & ((2u << gl) - 1u)); // lane 0 always starts a column
                         const bool hasRun = gl < totalRuns;
                         const int myCol = hasRun ? scratch[myStart] : c;
-                        const int k = gl - myStart;
+                        const int k = gl - myStart + (myCol == c ? k0 : 0);           // run index inside its column
                         __syncwarp(gmask);
                         const float cDl = GSHFL(myDl, myCol), cDn = GSHFL(myDn, myCol);
-                        const int colLod = GSHFL(myLod, myCol);
                         const uint32_t colOff = GSHFL(hdr.x, myCol);
                         const int colRuns = GSHFL(myRunCount, myCol);
+                        const uint32_t* colElems = world.lods[cLod].elements + colOff; // one LOD per batch
                         uint32_t el = 0u;
-                        if (hasRun) el = __ldg(world.lods[colLod].elements + colOff + (ITER > 0 ? 1 + k : colRuns - k));
-                        r_ci = (int)(short)(el & 0xffffu); r_len = (int)(short)(el >> 16); // RLEElement World.cs:245-259
-                        roundInvalid = GBALLOT(hasRun && r_len == 0);
+                        if (hasRun) el = __ldg(colElems + (ITER > 0 ? 1 + k : colRuns - k));
+                        r_ci = (int)(short)(el & 0xffffu); const int r_len = (int)(short)(el >> 16); // RLEElement World.cs:245-259
+                        roundInvalid = GBALLOT(hasRun && r_len == 0);  // an invalid element (Length == 0) ends its column (:445-447)
                         // lanes of my column from its start up to me, and whether an invalid element precedes me there
                         const uint32_t mineUpToMe = ((2u << gl) - 1u) & ~((1u << myStart) - 1u);
                         const bool valid = hasRun && !(roundInvalid & mineUpToMe);
-                        const int span = valid ? r_len * (1 << colLod) : 0;
+                        const int span = valid ? r_len * cScale : 0;
                         int sum = span;
 #pragma unroll
                         for (int o = 1; o < G; o <<= 1) { int t = __shfl_up_sync(gmask, sum, o, G); if (gl >= o) sum += t; }
                         const int before = GSHFL(sum, myStart > 0 ? myStart - 1 : 0);
-                        const int inclCol = sum - (myStart > 0 ? before : 0); // runs of my column up to and including me
+                        const int inclCol = sum - (myStart > 0 ? before : 0) + (myCol == c ? yDone : 0); // my column's runs up to and including me
+                        if (tall) yDone = GSHFL(inclCol, runsHere - 1);                // extent after this pass (the round holds only this column)
                         if (ITER > 0) { r_eMax = (float)(world.dim_y - (inclCol - span)); r_eMin = (float)(world.dim_y - inclCol); } // :449-455
                         else          { r_eMin = (float)(inclCol - span); r_eMax = (float)inclCol; }
 
                         STAMP(5);
-                        const F3 lMinLast = F3{planeBottom.x + planeDir.x * cDl, planeBottom.y + planeDir.y * cDl, planeBottom.z + planeDir.z * cDl};
+                        const F3 lMinLast = F3{planeBottom.x + planeDir.x * cDl, planeBottom.y + planeDir.y * cDl, planeBottom.z + planeDir.z * cDl}; // :289-293
                         const F3 lMinNext = F3{planeBottom.x + planeDir.x * cDn, planeBottom.y + planeDir.y * cDn, planeBottom.z + planeDir.z * cDn};
                         const F3 lMaxLast = F3{planeTop.x + planeDir.x * cDl, planeTop.y + planeDir.y * cDl, planeTop.z + planeDir.z * cDl};
                         const F3 lMaxNext = F3{planeTop.x + planeDir.x * cDn, planeTop.y + planeDir.y * cDn, planeTop.z + planeDir.z * cDn};
                         r_sideClip = false; r_capClip = false; r_capKind = 0;
                         {
+                            float bfx = 0.0f, bfy = 0.0f, uvAx = 0.0f, uvAy = 0.0f, uvBx = 0.0f, uvBy = 0.0f;
+                            int capIdx = 0;
                             const float portionBottom = unlerpf(0.0f, worldMaxY, r_eMin); // :478-481
                             const float portionTop = unlerpf(0.0f, worldMaxY, r_eMax);
                             F3 frontBottom = lerp3(lMinLast, lMaxLast, portionBottom);
                             F3 frontTop = lerp3(lMinLast, lMaxLast, portionTop);
+                            // which cap, if any, depends on the camera height only (:549,556); its flat colour (:553,560) is fetched
+                            // now, while the divisions below run, and parked in the cache
+                            if (portionTop < cameraPosYNormalized) { r_capKind = 1; capIdx = r_ci; }
+                            else if (portionBottom > cameraPosYNormalized) { r_capKind = 2; capIdx = r_ci + r_len - 1; }
+                            uint32_t capColor = 0u;
+                            if (r_capKind && valid && r_ci >= 0) capColor = __ldg(colElems + colRuns + 2 + capIdx);
                             float uA = (float)r_len, uB = 0.0f;
                             if (clip_near_u(frontBottom, frontTop, uA, uB)) { // :489-502 (clips frontBottom/Top in place)
-                                r_uvAx = 1.0f / frontBottom.z; r_uvAy = uA / frontBottom.z;
-                                r_uvBx = 1.0f / frontTop.z;    r_uvBy = uB / frontTop.z;
-                                r_bfx = frontBottom.x / frontBottom.z; r_bfy = frontTop.x / frontTop.z;
-                                if (r_bfx > r_bfy) {
-                                    float t = r_bfx; r_bfx = r_bfy; r_bfy = t;
-                                    t = r_uvAx; r_uvAx = r_uvBx; r_uvBx = t;
-                                    t = r_uvAy; r_uvAy = r_uvBy; r_uvBy = t;
+                                uvAx = 1.0f / frontBottom.z; uvAy = uA / frontBottom.z;
+                                uvBx = 1.0f / frontTop.z;    uvBy = uB / frontTop.z;
+                                bfx = frontBottom.x / frontBottom.z; bfy = frontTop.x / frontTop.z;
+                                if (bfx > bfy) {
+                                    float t = bfx; bfx = bfy; bfy = t;
+                                    t = uvAx; uvAx = uvBx; uvBx = t;
+                                    t = uvAy; uvAy = uvBy; uvBy = t;
                                 }
-                                r_sMin = f2i(rintf(r_bfx)); r_sMax = f2i(rintf(r_bfy));
+                                r_sMin = f2i(rintf(bfx)); r_sMax = f2i(rintf(bfy));
                                 r_sideClip = true;
                             }
-                            F3 secA = frontTop, secB = frontTop; // :544-565; which cap, if any, depends on the camera height only
-                            if (portionTop < cameraPosYNormalized) { r_capKind = 1; r_capIdx = r_ci; secA = lerp3(lMinNext, lMaxNext, portionTop); secB = frontTop; }
-                            else if (portionBottom > cameraPosYNormalized) { r_capKind = 2; r_capIdx = r_ci + r_len - 1; secA = lerp3(lMinNext, lMaxNext, portionBottom); secB = frontBottom; }
-                            if (r_capKind && clip_near(secA, secB)) { // :568-578
-                                r_cMin = f2i(rintf(secA.x / secA.z)); r_cMax = f2i(rintf(secB.x / secB.z));
-                                if (r_cMin > r_cMax) { int t = r_cMin; r_cMin = r_cMax; r_cMax = t; }
-                                r_capClip = true;
+                            if (r_capKind) { // :554-578
+                                const float portion = r_capKind == 1 ? portionTop : portionBottom;
+                                F3 secA = lerp3(lMinNext, lMaxNext, portion), secB = r_capKind == 1 ? frontTop : frontBottom;
+                                if (clip_near(secA, secB)) {
+                                    r_cMin = f2i(rintf(secA.x / secA.z)); r_cMax = f2i(rintf(secB.x / secB.z));
+                                    if (r_cMin > r_cMax) { int t = r_cMin; r_cMin = r_cMax; r_cMax = t; }
+                                    r_capClip = true;
+                                }
                             }
+                            cache[0 * G + gl] = __float_as_uint(bfx);  cache[1 * G + gl] = __float_as_uint(bfy);
+                            cache[2 * G + gl] = __float_as_uint(uvAx); cache[3 * G + gl] = __float_as_uint(uvAy);
+                            cache[4 * G + gl] = __float_as_uint(uvBx); cache[5 * G + gl] = __float_as_uint(uvBy);
+                            cache[6 * G + gl] = (uint32_t)r_len;       cache[7 * G + gl] = capColor;
+                            __syncwarp(gmask);
                         }
                         STAMP(4);
                     }
 
-                    // ---- resolve column c against the current frustum / written-pixel state (:441-611) --------------------
+                    // ---- resolve this column (pass) against the current frustum / written-pixel state (:441-611) -----------
                     const int base = GSHFL(myBase, c);
-                    const uint32_t colMask = (runCount >= 32 ? FULL_MASK : ((1u << runCount) - 1u)) << base;
+                    const uint32_t colMask = (runsHere >= 32 ? FULL_MASK : ((1u << runsHere) - 1u)) << base;
                     const bool inCol = (colMask >> gl) & 1u;
                     const uint32_t invalidHere = roundInvalid & colMask;
-                    const int endValid = invalidHere ? __ffs(invalidHere) - 1 : base + runCount; // first lane past the valid runs
-                    const bool valid = inCol && gl < endValid;
-                    const bool solid = valid && r_ci >= 0; // !IsAir
+                    const int endValid = invalidHere ? __ffs(invalidHere) - 1 : base + runsHere; // first lane past the valid runs
+                    const bool solid = inCol && gl < endValid && r_ci >= 0; // valid and !IsAir
                     const bool above = r_eMin > worldBoundsMax, below = r_eMax < worldBoundsMin;
                     const bool isBreak = solid && (ITER > 0 ? (!above && below) : above); // :461-475 (above is tested first)
                     const uint32_t breakMask = GBALLOT(isBreak);
                     const int endVisit = breakMask ? __ffs(breakMask) : endValid;           // the breaking run itself was dereferenced
+                    if (invalidHere | breakMask) colStop = true;
                     const bool active = solid && gl < endVisit && !above && !below;
                     const bool sideOk = active && r_sideClip;
                     const bool capOk = active && r_capClip &&
                                        (r_capKind == 1 ? !(r_eMax > worldBoundsMax) : !(r_eMin < worldBoundsMin)); // :549-565
 
                     STAMP(6);
-                    // ---- commit, in reference order, only the spans that still hold an unwritten pixel ----------
-                    uint32_t pending = GBALLOT(sideOk || capOk);
+                    // ---- commit, in reference order (side of run j, cap of run j, side of run j+1, ...), only the spans that still
+                    // hold an unwritten pixel; everything ordered before the committed span is a no-op now and stays one (written
+                    // pixels only grow, the writable range only shrinks), so it is retired with it.
+                    uint32_t pendingS = GBALLOT(sideOk), pendingC = GBALLOT(capOk);
                     int visitedHere = endVisit - base;
-                    while (pending) {
-                        const bool wSide = sideOk && span_would_write(rw, r_sMin, r_sMax);
-                        const bool wCap = capOk && span_would_write(rw, r_cMin, r_cMax);
-                        const uint32_t hot = GBALLOT(wSide || wCap) & pending;
-                        if (!hot) break;
-                        const int j = __ffs(hot) - 1;
-                        pending &= ~((2u << j) - 1u);
-                        if (GSHFL((int)wSide, j)) { // side of run j :505-540
-                            int bMin = GSHFL(r_sMin, j), bMax = GSHFL(r_sMax, j);
-                            reduce_pixel_horizon(rw, bMin, bMax);
-                            const float jbfx = GSHFL(r_bfx, j), jbfy = GSHFL(r_bfy, j);
-                            const float jAx = GSHFL(r_uvAx, j), jAy = GSHFL(r_uvAy, j);
-                            const float jBx = GSHFL(r_uvBx, j), jBy = GSHFL(r_uvBy, j);
-                            const int jLen = GSHFL(r_len, j), jCi = GSHFL(r_ci, j);
+                    while (pendingS | pendingC) {
+                        const uint32_t hotS = GBALLOT(((pendingS >> gl) & 1u) && span_would_write(rw, r_sMin, r_sMax));
+                        const uint32_t hotC = GBALLOT(((pendingC >> gl) & 1u) && span_would_write(rw, r_cMin, r_cMax));
+                        if (!(hotS | hotC)) break;
+                        const int jS = hotS ? __ffs(hotS) - 1 : 64, jC = hotC ? __ffs(hotC) - 1 : 64;
+                        const bool isCap = jC < jS;
+                        const int j = isCap ? jC : jS;
+                        pendingS &= ~((2u << j) - 1u);
+                        pendingC &= isCap ? ~((2u << j) - 1u) : ~((1u << j) - 1u);
+                        int bMin = GSHFL(isCap ? r_cMin : r_sMin, j), bMax = GSHFL(isCap ? r_cMax : r_sMax, j);
+                        reduce_pixel_horizon(rw, bMin, bMax); // :507-517 / :583-593
+                        if (isCap) {
+                            const uint32_t color = cache[7 * G + j];
+                            for (int y = bMin + gl; y <= bMax; y += G) // :595-602
+                                if (!((rw.seen[y >> 5] >> (y & 31)) & 1u)) row[y] = color;
+                        } else {
+                            const float jbfx = __uint_as_float(cache[0 * G + j]), jbfy = __uint_as_float(cache[1 * G + j]);
+                            const float jAx = __uint_as_float(cache[2 * G + j]), jAy = __uint_as_float(cache[3 * G + j]);
+                            const float jBx = __uint_as_float(cache[4 * G + j]), jBy = __uint_as_float(cache[5 * G + j]);
+                            const int jLen = (int)cache[6 * G + j], jCi = GSHFL(r_ci, j);
                             for (int y = bMin + gl; y <= bMax; y += G) { // :519-533
                                 if (!((rw.seen[y >> 5] >> (y & 31)) & 1u)) {
                                     float l = unlerpf(jbfx, jbfy, (float)y);
                                     float wx = lerpf(jAx, jBx, l), wy = lerpf(jAy, jBy, l);
                                     float u = wy / wx;
                                     int idx = max(0, min(jLen - 1, f2i(floorf(u)))) + jCi;
-                                    row[y] = __ldg(colColors + idx);
+                                    if (pendY >= 0) row[pendY] = pendColor; // the gather issued by the previous commit has long arrived
+                                    pendColor = __ldg(colColors + idx); pendY = y;
                                 }
                             }
-                            __syncwarp(gmask);
-                            for (int w = (bMin >> 5) + gl; w <= (bMax >> 5); w += G) {
-                                uint32_t m = FULL_MASK;
-                                if (w == (bMin >> 5)) m &= mask_from(bMin);
-                                if (w == (bMax >> 5)) m &= mask_to(bMax);
-                                const uint32_t old = rw.seen[w];
-                                if (COUNTERS) acc.px_voxel += __popc(~old & m);
-                                rw.seen[w] = old | m;
-                            }
-                            __syncwarp(gmask);
-                            frustumDirMaxWorld = EPS; // a pixel was written (:522)
-                            if (rw.nf_min > rw.nf_max) { terminated = true; visitedHere = j + 1 - base; break; } // :535-539
                         }
-                        // cap of run j :581-609, re-tested against the state the side span left behind
-                        const bool wCapNow = capOk && span_would_write(rw, r_cMin, r_cMax);
-                        if (GSHFL((int)wCapNow, j)) {
-                            int bMin = GSHFL(r_cMin, j), bMax = GSHFL(r_cMax, j);
-                            reduce_pixel_horizon(rw, bMin, bMax);
-                            const uint32_t color = __ldg(colColors + GSHFL(r_capIdx, j));
-                            for (int y = bMin + gl; y <= bMax; y += G) // :595-602
-                                if (!((rw.seen[y >> 5] >> (y & 31)) & 1u)) row[y] = color;
-                            __syncwarp(gmask);
-                            for (int w = (bMin >> 5) + gl; w <= (bMax >> 5); w += G) {
-                                uint32_t m = FULL_MASK;
-                                if (w == (bMin >> 5)) m &= mask_from(bMin);
-                                if (w == (bMax >> 5)) m &= mask_to(bMax);
-                                const uint32_t old = rw.seen[w];
-                                if (COUNTERS) acc.px_voxel += __popc(~old & m);
-                                rw.seen[w] = old | m;
-                            }
-                            __syncwarp(gmask);
-                            frustumDirMaxWorld = EPS; // :598
-                            if (rw.nf_min > rw.nf_max) { terminated = true; visitedHere = j + 1 - base; break; } // :604-608
-                        }
+                        __syncwarp(gmask);
+                        { const int fresh = mark_seen<G>(rw.seen, rw.full, bMin, bMax, gl); if (COUNTERS) acc.px_voxel += fresh; }
+                        __syncwarp(gmask);
+                        frustumDirMaxWorld = EPS; // a pixel was written (:522,598)
+                        if (rw.nf_min > rw.nf_max) { terminated = true; visitedHere = j + 1 - base; break; } // :535-539,604-608
                     }
                     if (COUNTERS && gl == 0) acc.runs_visited += visitedHere;
-                    STAMP(4);
-                } else {
-                // ================= columns with more than G runs: G runs per pass ==========================================
+                    if (tall) { k0 += G; roundCols = 0u; } // the cache held one pass of this column only
+                } while (tall && k0 < runCount && !colStop && !terminated);
                 STAMP(4);
-                roundCols = 0u; // the pass below reuses nothing of the cache and the cache is not valid for this column
-                int chunkStartY = ITER > 0 ? world.dim_y : 0;                 // running elementBounds, exact in int
-                bool colStop = false;
-                for (int k0 = 0; k0 < runCount && !colStop && !terminated; k0 += G) {
-                    const int k = k0 + gl;
-                    const bool inCol = k < runCount;
-                    uint32_t el = inCol ? __ldg(colBase + (ITER > 0 ? 1 + k : runCount - k)) : 0u;
-                    const int ci = (int)(short)(el & 0xffffu), len = (int)(short)(el >> 16); // RLEElement World.cs:245-259
-                    // an invalid element (Length == 0) ends the column (:445-447)
-                    const uint32_t invalidMask = GBALLOT(!inCol || len == 0);
-                    const int nValid = invalidMask ? __ffs(invalidMask) - 1 : G;
-                    const bool valid = gl < nValid;
-                    int span = valid ? len * cScale : 0;
-                    int incl = span;
-#pragma unroll
-                    for (int o = 1; o < G; o <<= 1) { int v = __shfl_up_sync(gmask, incl, o, G); if (gl >= o) incl += v; }
-                    const int chunkTotal = GSHFL(incl, G - 1);
-                    float eMin, eMax; // elementBoundsMin/Max :449-455
-                    if (ITER > 0) { eMax = (float)(chunkStartY - (incl - span)); eMin = (float)(chunkStartY - incl); }
-                    else          { eMin = (float)(chunkStartY + (incl - span)); eMax = (float)(chunkStartY + incl); }
-                    chunkStartY += ITER > 0 ? -chunkTotal : chunkTotal;
-                    if (nValid < G && (k0 + nValid) < runCount) colStop = true; // hit an invalid element inside the column
-
-                    const bool solid = valid && ci >= 0; // !IsAir
-                    const bool above = eMin > worldBoundsMax, below = eMax < worldBoundsMin;
-                    const bool isBreak = solid && (ITER > 0 ? (!above && below) : above); // :461-475 (above is tested first)
-                    const uint32_t breakMask = GBALLOT(isBreak);
-                    int nVisit = nValid;
-                    if (breakMask) { nVisit = __ffs(breakMask); colStop = true; } // the breaking run itself was dereferenced
-                    const bool active = solid && gl < nVisit && !above && !below;
-
-                    STAMP(5);
-                    // ---- per-lane span geometry; depends only on column constants ------------------------------
-                    bool sideOk = false, capOk = false;
-                    int sMin = 0, sMax = 0, cMin = 0, cMax = 0, capIdx = 0;
-                    float bfx = 0.0f, bfy = 0.0f, uvAx = 0.0f, uvAy = 0.0f, uvBx = 0.0f, uvBy = 0.0f;
-                    if (active) {
-                        float portionBottom = unlerpf(0.0f, worldMaxY, eMin); // :478-481
-                        float portionTop = unlerpf(0.0f, worldMaxY, eMax);
-                        F3 frontBottom = lerp3(minLast, maxLast, portionBottom);
-                        F3 frontTop = lerp3(minLast, maxLast, portionTop);
-                        float uA = (float)len, uB = 0.0f;
-                        if (clip_near_u(frontBottom, frontTop, uA, uB)) { // :489-502 (clips frontBottom/Top in place)
-                            uvAx = 1.0f / frontBottom.z; uvAy = uA / frontBottom.z;
-                            uvBx = 1.0f / frontTop.z;    uvBy = uB / frontTop.z;
-                            bfx = frontBottom.x / frontBottom.z; bfy = frontTop.x / frontTop.z;
-                            if (bfx > bfy) {
-                                float t = bfx; bfx = bfy; bfy = t;
-                                t = uvAx; uvAx = uvBx; uvBx = t;
-                                t = uvAy; uvAy = uvBy; uvBy = t;
-                            }
-                            sMin = f2i(rintf(bfx)); sMax = f2i(rintf(bfy));
-                            sideOk = true;
-                        }
-                        F3 secA, secB; bool cap = false; // :544-565
-                        if (portionTop < cameraPosYNormalized) {
-                            if (!(eMax > worldBoundsMax)) { cap = true; capIdx = ci; secA = lerp3(minNext, maxNext, portionTop); secB = frontTop; }
-                        } else if (portionBottom > cameraPosYNormalized) {
-                            if (!(eMin < worldBoundsMin)) { cap = true; capIdx = ci + len - 1; secA = lerp3(minNext, maxNext, portionBottom); secB = frontBottom; }
-                        }
-                        if (cap && clip_near(secA, secB)) { // :568-578
-                            cMin = f2i(rintf(secA.x / secA.z)); cMax = f2i(rintf(secB.x / secB.z));
-                            if (cMin > cMax) { int t = cMin; cMin = cMax; cMax = t; }
-                            capOk = true;
-                        }
-                    }
-
-                    STAMP(6);
-                    // ---- commit, in reference order, only the spans that still hold an unwritten pixel ----------
-                    uint32_t pending = GBALLOT(sideOk || capOk);
-                    int visitedHere = nVisit;
-                    while (pending) {
-                        const bool wSide = sideOk && span_would_write(rw, sMin, sMax);
-                        const bool wCap = capOk && span_would_write(rw, cMin, cMax);
-                        const uint32_t hot = GBALLOT(wSide || wCap) & pending;
-                        if (!hot) break;
-                        const int j = __ffs(hot) - 1;
-                        pending &= ~((2u << j) - 1u);
-                        if (GSHFL((int)wSide, j)) { // side of run j :505-540
-                            int bMin = GSHFL(sMin, j), bMax = GSHFL(sMax, j);
-                            reduce_pixel_horizon(rw, bMin, bMax);
-                            const float jbfx = GSHFL(bfx, j), jbfy = GSHFL(bfy, j);
-                            const float jAx = GSHFL(uvAx, j), jAy = GSHFL(uvAy, j);
-                            const float jBx = GSHFL(uvBx, j), jBy = GSHFL(uvBy, j);
-                            const int jLen = GSHFL(len, j), jCi = GSHFL(ci, j);
-                            for (int y = bMin + gl; y <= bMax; y += G) { // :519-533
-                                if (!((rw.seen[y >> 5] >> (y & 31)) & 1u)) {
-                                    float l = unlerpf(jbfx, jbfy, (float)y);
-                                    float wx = lerpf(jAx, jBx, l), wy = lerpf(jAy, jBy, l);
-                                    float u = wy / wx;
-                                    int idx = max(0, min(jLen - 1, f2i(floorf(u)))) + jCi;
-                                    row[y] = __ldg(colColors + idx);
-                                }
-                            }
-                            __syncwarp(gmask);
-                            for (int w = (bMin >> 5) + gl; w <= (bMax >> 5); w += G) {
-                                uint32_t m = FULL_MASK;
-                                if (w == (bMin >> 5)) m &= mask_from(bMin);
-                                if (w == (bMax >> 5)) m &= mask_to(bMax);
-                                const uint32_t old = rw.seen[w];
-                                if (COUNTERS) acc.px_voxel += __popc(~old & m);
-                                rw.seen[w] = old | m;
-                            }
-                            __syncwarp(gmask);
-                            frustumDirMaxWorld = EPS; // a pixel was written (:522)
-                            if (rw.nf_min > rw.nf_max) { terminated = true; visitedHere = j + 1; break; } // :535-539
-                        }
-                        // cap of run j :581-609, re-tested against the state the side span left behind
-                        const bool wCapNow = capOk && span_would_write(rw, cMin, cMax);
-                        if (GSHFL((int)wCapNow, j)) {
-                            int bMin = GSHFL(cMin, j), bMax = GSHFL(cMax, j);
-                            reduce_pixel_horizon(rw, bMin, bMax);
-                            const uint32_t color = __ldg(colColors + GSHFL(capIdx, j));
-                            for (int y = bMin + gl; y <= bMax; y += G) // :595-602
-                                if (!((rw.seen[y >> 5] >> (y & 31)) & 1u)) row[y] = color;
-                            __syncwarp(gmask);
-                            for (int w = (bMin >> 5) + gl; w <= (bMax >> 5); w += G) {
-                                uint32_t m = FULL_MASK;
-                                if (w == (bMin >> 5)) m &= mask_from(bMin);
-                                if (w == (bMax >> 5)) m &= mask_to(bMax);
-                                const uint32_t old = rw.seen[w];
-                                if (COUNTERS) acc.px_voxel += __popc(~old & m);
-                                rw.seen[w] = old | m;
-                            }
-                            __syncwarp(gmask);
-                            frustumDirMaxWorld = EPS; // :598
-                            if (rw.nf_min > rw.nf_max) { terminated = true; visitedHere = j + 1; break; } // :604-608
-                        }
-                    }
-                    if (COUNTERS && gl == 0) acc.runs_visited += visitedHere;
-                    STAMP(4);
-                }
-                }
                 if (terminated) { cellsDone = c + 1; break; }
             }
             if (COUNTERS && gl == 0) acc.dda_steps += cellsDone;
             if (endKind != 0) reachedEnd = true;
         }
+        if (pendY >= 0) row[pendY] = pendColor;
         STAMP(7);
         // WriteSkybox :699-708 — :248,268,323,401,419,537,606,619 all end here
         __syncwarp(gmask);
@@ -956,7 +933,7 @@ static cudaError_t launch_phase1_g(const cvxd_world& world, const cvxd_frame& fr
     constexpr int groupsPerCta = CVXD_THREADS_PER_CTA / G;
     const int blocks = (n + groupsPerCta - 1) / groupsPerCta;
     const int seenWords = ((frame.width > frame.height ? frame.width : frame.height) + 31) >> 5;
-    const size_t smem = (size_t)groupsPerCta * (seenWords + G) * sizeof(uint32_t);
+    const size_t smem = (size_t)groupsPerCta * (seenWords + ((seenWords + 31) >> 5) + 9 * G) * sizeof(uint32_t);
     if (frame.timing) {
         if (G == 32) phase1_kernel<32, false, true><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
         else return cudaErrorInvalidValue; // the timing build exists for the default group width only

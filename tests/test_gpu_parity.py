@@ -37,12 +37,24 @@ def _oracle_frame(orc, ow, s, W, H, fill):
 
 
 def _gpu_frame(rm, s, fill):
+    """Renders twice: with the work counters on (every column the reference enters is entered, so the counts are exact)
+    and in the product configuration (counters compiled out, columns that provably cannot write are skipped); the pixels of
+    both must be identical, and the caller compares them and the counters with the oracle."""
     rm.clear_raybuffers(fill)
     rm.counters()
     rm.draw_setup(s)
     rm.sync()
     td, lr = rm.read_raybuffers()
-    return td, lr, rm.counters(), rm.read_frame()
+    cn, frame = rm.counters(), rm.read_frame()
+    rm.set_counters(False)
+    rm.clear_raybuffers(fill)
+    rm.draw_setup(s)
+    rm.sync()
+    td2, lr2 = rm.read_raybuffers()
+    frame2 = rm.read_frame()
+    rm.set_counters(True)
+    assert np.array_equal(td, td2) and np.array_equal(lr, lr2) and np.array_equal(frame, frame2), "product build differs from counter build"
+    return td, lr, cn, frame
 
 
 def _assert_same(g, o, what):
