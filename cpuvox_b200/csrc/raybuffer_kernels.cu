@@ -581,50 +581,44 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                     const bool A = pMin.x > pMin.z * rw.fb_max, B = pMax.x > pMax.z * rw.fb_max;
                     const bool C = pMin.x < pMin.z * rw.fb_min, D = pMax.x < pMax.z * rw.fb_min;
                     const bool clipped = (A && B) || (!A && !B && C && D);
-                    float myLerp;
-                    if (L & 1) myLerp = B ? clip_max(pMin, pMax, rw.fb_max) : (D ? clip_max(pMin, pMax, rw.fb_min) : 1.0f);
-                    else       myLerp = A ? clip_min(pMin, pMax, rw.fb_max) : (C ? clip_min(pMin, pMax, rw.fb_min) : 0.0f);
+                    // ClipMin / ClipMax (CameraData.cs:101-115) against whichever frustum bound this lane's end crosses, if any
+                    const bool isMax = L & 1;
+                    const bool crossHi = isMax ? B : A, crossLo = isMax ? D : C;
+                    float myLerp = isMax ? 1.0f : 0.0f;
+                    if (crossHi || crossLo) {
+                        const float fi = 1.0f / (crossHi ? rw.fb_max : rw.fb_min);
+                        const float c0 = cross2(1.0f, fi, pMax.x, pMax.z), c1 = cross2(1.0f, fi, pMin.x, pMin.z);
+                        const float q = isMax ? c1 / (c1 - c0) : c0 / (c0 - c1);
+                        myLerp = isMax ? q : 1.0f - q;
+                    }
                     const F3 pc = lerp3(pMin, pMax, myLerp);
                     const float myProj = pc.x / pc.z;
                     const float lastMinL = GSHFL(myLerp, 0), lastMaxL = GSHFL(myLerp, 1), nextMinL = GSHFL(myLerp, 2), nextMaxL = GSHFL(myLerp, 3);
                     float mnL = GSHFL(myProj, 0), mxL = GSHFL(myProj, 1), mnN = GSHFL(myProj, 2), mxN = GSHFL(myProj, 3);
                     const bool clippedLast = GSHFL((int)clipped, 0) != 0, clippedNext = GSHFL((int)clipped, 2) != 0;
-                    float clippedMin, clippedMax;
+                    float clippedMin, clippedMax, distForMin, distForMax; // which line's distance each frustum direction is taken at
                     if (clippedLast) {
                         if (clippedNext) { terminated = true; cellsDone = c + 1; break; }
-                        worldBoundsMin = lerpf(0.0f, worldMaxY, nextMinL);
-                        worldBoundsMax = lerpf(0.0f, worldMaxY, nextMaxL);
-                        frustumDirMaxWorld = (worldBoundsMax - camY) / distNext;
-                        frustumDirMinWorld = (worldBoundsMin - camY) / distNext;
+                        worldBoundsMin = lerpf(0.0f, worldMaxY, nextMinL); distForMin = distNext;
+                        worldBoundsMax = lerpf(0.0f, worldMaxY, nextMaxL); distForMax = distNext;
                         clippedMin = mnN; clippedMax = mxN;
                         if (clippedMax < clippedMin) { float t = clippedMin; clippedMin = clippedMax; clippedMax = t; }
                     } else if (clippedNext) {
-                        worldBoundsMin = lerpf(0.0f, worldMaxY, lastMinL);
-                        worldBoundsMax = lerpf(0.0f, worldMaxY, lastMaxL);
-                        frustumDirMaxWorld = (worldBoundsMax - camY) / distLast;
-                        frustumDirMinWorld = (worldBoundsMin - camY) / distLast;
+                        worldBoundsMin = lerpf(0.0f, worldMaxY, lastMinL); distForMin = distLast;
+                        worldBoundsMax = lerpf(0.0f, worldMaxY, lastMaxL); distForMax = distLast;
                         clippedMin = mnL; clippedMax = mxL;
                         if (clippedMax < clippedMin) { float t = clippedMin; clippedMin = clippedMax; clippedMax = t; }
                     } else {
-                        if (lastMinL < nextMinL) {
-                            worldBoundsMin = lerpf(0.0f, worldMaxY, lastMinL);
-                            frustumDirMinWorld = (worldBoundsMin - camY) / distLast;
-                        } else {
-                            worldBoundsMin = lerpf(0.0f, worldMaxY, nextMinL);
-                            frustumDirMinWorld = (worldBoundsMin - camY) / distNext;
-                        }
-                        if (lastMaxL > nextMaxL) {
-                            worldBoundsMax = lerpf(0.0f, worldMaxY, lastMaxL);
-                            frustumDirMaxWorld = (worldBoundsMax - camY) / distLast;
-                        } else {
-                            worldBoundsMax = lerpf(0.0f, worldMaxY, nextMaxL);
-                            frustumDirMaxWorld = (worldBoundsMax - camY) / distNext;
-                        }
+                        const bool minFromLast = lastMinL < nextMinL, maxFromLast = lastMaxL > nextMaxL;
+                        worldBoundsMin = lerpf(0.0f, worldMaxY, minFromLast ? lastMinL : nextMinL); distForMin = minFromLast ? distLast : distNext;
+                        worldBoundsMax = lerpf(0.0f, worldMaxY, maxFromLast ? lastMaxL : nextMaxL); distForMax = maxFromLast ? distLast : distNext;
                         if (mxN < mnN) { float t = mxN; mxN = mnN; mnN = t; }
                         if (mxL < mnL) { float t = mxL; mxL = mnL; mnL = t; }
                         clippedMin = minf_(mnL, mnN);
                         clippedMax = maxf_(mxL, mxN);
                     }
+                    frustumDirMaxWorld = (worldBoundsMax - camY) / distForMax; // :329-330,348-349,359-370
+                    frustumDirMinWorld = (worldBoundsMin - camY) / distForMin;
                     worldBoundsMin = floorf(worldBoundsMin);
                     worldBoundsMax = ceilf(worldBoundsMax);
                     const int writableMin = f2i(floorf(clippedMin));
