@@ -1,0 +1,9 @@
+set -x
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv
+( time python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log
+python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_ref.json
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-1080p > gpurun_out/bench_under_ncu.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:phase1 -s 2 -c 2 -o gpurun_out/prof_phase1_4k python tools/one_frame.py --res 3840x2160 --poses 30,59 --reps 2 > gpurun_out/ncu_full.log 2>&1
+tail -3 gpurun_out/ncu_full.log
