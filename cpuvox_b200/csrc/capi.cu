@@ -16,6 +16,8 @@
 
 #include "../../include/cpuvox_b200.h"
 #include "device_types.h"
+#include "host_frame.h"
+#include "world_transcode.h"
 
 static_assert(sizeof(cvx_ray_state) == sizeof(cvxd_ray_state), "ray state layout");
 static_assert(sizeof(cvx_counters) == sizeof(cvxd_counters), "counter layout");
@@ -30,6 +32,8 @@ struct cvx_ctx {
     cvxd_world world;
     void* lodHeaders[CVX_LOD_LEVELS];
     void* lodElements[CVX_LOD_LEVELS];
+    void* lodBounds[CVX_LOD_LEVELS];
+    bool lodRegular[CVX_LOD_LEVELS];
     int width = 0, height = 0;
     uint32_t* td = nullptr;
     uint32_t* lr = nullptr;
@@ -69,41 +73,6 @@ int fail(cvx_ctx* ctx, int code, const char* fmt, ...) {
                         "%s failed: %s", #call, cudaGetErrorString(e_));                                  \
     } while (0)
 
-inline int f2i(float f) { return (f >= -2147483648.0f && f < 2147483648.0f) ? (int)f : (int)0x80000000; }
-inline int clampi(int x, int a, int b) { return x < a ? a : (x > b ? b : x); }
-
-// RenderManager.DrawSegments context fill, RenderManager.cs:281-318
-int fill_segments(const cvx_frame_setup* s, int W, int H, cvxd_segment out[4]) {
-    int total = 0;
-    const float vx = s->vanishing_point_screen[0], vy = s->vanishing_point_screen[1];
-    for (int k = 0; k < 4; k++) {
-        cvxd_segment& c = out[k];
-        memset(&c, 0, sizeof c);
-        const cvx_segment& in = s->segments[k];
-        c.ray_count = in.ray_count;
-        total += in.ray_count > 0 ? in.ray_count : 0;
-        for (int i = 0; i < 2; i++) {
-            c.ray_min[i] = in.cam_local_plane_ray_min[i]; c.ray_max[i] = in.cam_local_plane_ray_max[i];
-            c.min_screen[i] = in.min_screen[i]; c.max_screen[i] = in.max_screen[i];
-        }
-        if (in.ray_count <= 0) continue;
-        c.axis_mapped_to_y = k > 1 ? 0 : 1;
-        c.ray_index_offset = k == 1 ? s->segments[0].ray_count : (k == 3 ? s->segments[2].ray_count : 0);
-        if (k < 2) {
-            c.buffer = 0;
-            int v = clampi(f2i(rintf(vy)), 0, H - 1); // Mathf.RoundToInt, half-to-even
-            c.pix_min = k == 0 ? v : 0;
-            c.pix_max = k == 0 ? H - 1 : v;
-        } else {
-            c.buffer = 1;
-            int v = clampi(f2i(rintf(vx)), 0, W - 1);
-            c.pix_min = k == 3 ? 0 : v;
-            c.pix_max = k == 3 ? v : W - 1;
-        }
-    }
-    return total;
-}
-
 int validate_setup(cvx_ctx* ctx, const cvx_frame_setup* s, int total) {
     const int W = ctx->width, H = ctx->height;
     int tdRays = (s->segments[0].ray_count > 0 ? s->segments[0].ray_count : 0) + (s->segments[1].ray_count > 0 ? s->segments[1].ray_count : 0);
@@ -115,16 +84,7 @@ int validate_setup(cvx_ctx* ctx, const cvx_frame_setup* s, int total) {
 }
 
 void make_frame(cvx_ctx* ctx, const cvx_frame_setup* s, cvxd_frame& f) {
-    memset(&f, 0, sizeof f);
-    memcpy(f.wts, s->camera.world_to_screen, sizeof f.wts);
-    f.pos_x = s->camera.position_xz[0]; f.pos_z = s->camera.position_xz[1]; f.pos_y = s->camera.position_y;
-    f.inverse = s->camera.inverse_element_iteration_direction ? 1 : 0;
-    f.far_clip = s->camera.far_clip;
-    memcpy(f.lod_dist, s->camera.lod_distances, sizeof f.lod_dist);
-    f.total_rays = fill_segments(s, ctx->width, ctx->height, f.seg);
-    f.vp_x = s->vanishing_point_screen[0]; f.vp_y = s->vanishing_point_screen[1];
-    f.width = ctx->width; f.height = ctx->height;
-    f.ray_begin = 0; f.ray_end = f.total_rays;
+    cvxh::frame_from_setup(s, ctx->width, ctx->height, f);
     f.td = ctx->td; f.lr = ctx->lr;
     f.counters = (ctx->flags & CVX_FLAG_COUNTERS) ? ctx->counters : nullptr;
 }
@@ -158,8 +118,9 @@ void free_resolution(cvx_ctx* ctx) {
 
 void free_world(cvx_ctx* ctx) {
     for (int i = 0; i < CVX_LOD_LEVELS; i++) {
-        cudaFree(ctx->lodHeaders[i]); cudaFree(ctx->lodElements[i]);
-        ctx->lodHeaders[i] = ctx->lodElements[i] = nullptr;
+        cudaFree(ctx->lodHeaders[i]); cudaFree(ctx->lodElements[i]); cudaFree(ctx->lodBounds[i]);
+        ctx->lodHeaders[i] = ctx->lodElements[i] = ctx->lodBounds[i] = nullptr;
+        ctx->lodRegular[i] = false;
     }
     memset(&ctx->world, 0, sizeof ctx->world);
 }
@@ -184,6 +145,8 @@ int cvx_create(const cvx_config* config, cvx_ctx** out_ctx) {
     memset(&ctx->world, 0, sizeof ctx->world);
     memset(ctx->lodHeaders, 0, sizeof ctx->lodHeaders);
     memset(ctx->lodElements, 0, sizeof ctx->lodElements);
+    memset(ctx->lodBounds, 0, sizeof ctx->lodBounds);
+    memset(ctx->lodRegular, 0, sizeof ctx->lodRegular);
 #define CREATE_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(nullptr, CVX_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); cvx_destroy(ctx); return CVX_ERR_CUDA; } } while (0)
     CREATE_CU(cudaSetDevice(dev));
     CREATE_CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -248,40 +211,38 @@ int cvx_world_upload(cvx_ctx* ctx, int32_t lod, int32_t dim_x, int32_t dim_y, in
     if (ctx->world.lod_count > 0 && (ctx->world.dim_x != dim_x || ctx->world.dim_y != dim_y || ctx->world.dim_z != dim_z))
         return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "LOD %d dimensions differ from the already uploaded world; call cvx_world_free first", lod);
     const int64_t elementCells = (bytes - headerBytes) / 4;
-    // validate on the host what the kernels index with: offsets + run counts must stay inside the element area
-    {
-        const uint8_t* p = (const uint8_t*)blob;
-        for (int64_t i = 0; i < needCols; i++) {
-            int32_t off; uint16_t rc;
-            memcpy(&off, p + 12 * i, 4); memcpy(&rc, p + 12 * i + 4, 2);
-            if (rc == 0) continue;
-            if (off < 0 || (int64_t)off + rc + 2 > elementCells) return fail(ctx, CVX_ERR_FORMAT, "column %lld of LOD %d points outside the element area", (long long)i, lod);
-        }
-    }
+    // transcode on the host (world_transcode.h); it also validates what the kernels index with: offsets + run counts must
+    // stay inside the element area
+    cvxh_lod_tables tables;
+    if (!cvxh_transcode_lod(blob, needCols, column_count, elementCells, lod, dim_y, tables))
+        return fail(ctx, CVX_ERR_FORMAT, "column %lld of LOD %d points outside the element area", (long long)tables.bad_column, lod);
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->lodHeaders[lod]); cudaFree(ctx->lodElements[lod]);
-    ctx->lodHeaders[lod] = ctx->lodElements[lod] = nullptr;
-    void* staging = nullptr;
-    CU(ctx, cudaMalloc(&staging, (size_t)headerBytes));
+    cudaFree(ctx->lodHeaders[lod]); cudaFree(ctx->lodElements[lod]); cudaFree(ctx->lodBounds[lod]);
+    ctx->lodHeaders[lod] = ctx->lodElements[lod] = ctx->lodBounds[lod] = nullptr;
+    const size_t boundBytes = tables.bounds.size() * sizeof(cvxh_u2);
     cudaError_t e = cudaMalloc(&ctx->lodHeaders[lod], (size_t)(16 * needCols));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->lodElements[lod], (size_t)(elementCells > 0 ? 4 * elementCells : 4));
-    if (e == cudaSuccess) e = cudaMemcpyAsync(staging, blob, (size_t)(12 * needCols), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->lodBounds[lod], boundBytes ? boundBytes : 8);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->lodHeaders[lod], tables.headers.data(), (size_t)(16 * needCols), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && elementCells > 0) e = cudaMemcpyAsync(ctx->lodElements[lod], (const uint8_t*)blob + headerBytes, (size_t)(4 * elementCells), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) { e = cvxd_launch_transcode_headers((const uint8_t*)staging, (uint4*)ctx->lodHeaders[lod], (const uint32_t*)ctx->lodElements[lod], needCols, ctx->stream); ctx->launches++; }
+    if (e == cudaSuccess && boundBytes) e = cudaMemcpyAsync(ctx->lodBounds[lod], tables.bounds.data(), boundBytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(staging);
     if (e != cudaSuccess) {
-        cudaFree(ctx->lodHeaders[lod]); cudaFree(ctx->lodElements[lod]);
-        ctx->lodHeaders[lod] = ctx->lodElements[lod] = nullptr;
+        cudaFree(ctx->lodHeaders[lod]); cudaFree(ctx->lodElements[lod]); cudaFree(ctx->lodBounds[lod]);
+        ctx->lodHeaders[lod] = ctx->lodElements[lod] = ctx->lodBounds[lod] = nullptr;
         return fail(ctx, e == cudaErrorMemoryAllocation ? CVX_ERR_OUT_OF_MEMORY : CVX_ERR_CUDA, "world upload failed: %s", cudaGetErrorString(e));
     }
     ctx->world.dim_x = dim_x; ctx->world.dim_y = dim_y; ctx->world.dim_z = dim_z;
     cvxd_lod& l = ctx->world.lods[lod];
     l.headers = (const uint4*)ctx->lodHeaders[lod];
     l.elements = (const uint32_t*)ctx->lodElements[lod];
+    l.bounds = (const uint2*)ctx->lodBounds[lod];
     l.mul_x = dim_z >> lod;
     l.lod = lod;
+    ctx->lodRegular[lod] = tables.regular;
+    ctx->world.regular = 1;
+    for (int i = 0; i < CVX_LOD_LEVELS; i++) if (ctx->lodHeaders[i] && !ctx->lodRegular[i]) ctx->world.regular = 0;
     if (lod + 1 > ctx->world.lod_count) ctx->world.lod_count = lod + 1;
     return CVX_OK;
 }

@@ -11,17 +11,19 @@
 #define CVXD_THREADS_PER_CTA 128
 #define CVXD_TIMING_REGIONS 8
 
-/* Device copy of one World LOD (Assets/Code/World.cs:8-43,161-188). Headers are transcoded at upload from the
- * reference's 12-byte RLEColumn into one 16-byte aligned uint4 per column so a lane fetches a column header with
- * a single 128-bit load:
- *   x = element offset (in 4-byte cells, relative to `elements`)
- *   y = runCount | worldMin << 16
- *   z = worldMax
- *   w = first RLEElement after the start guard (lets 1-run lookups skip a dependent load; 0 when empty)
- * `elements` is the reference element area verbatim: [guard][runs...][guard][ColorARGB32...] per column. */
+/* Device copy of one World LOD (Assets/Code/World.cs:8-43,161-188), transcoded on the host at upload (world_transcode.h):
+ *   headers   one 16-byte aligned uint4 per column, fetched by a lane with a single 128-bit load:
+ *               x = element offset (in 4-byte cells, relative to `elements`)
+ *               y = runCount | worldMin << 16
+ *               z = worldMax
+ *               w = offset of the column's first boundary record in `bounds`
+ *   elements  the reference element area verbatim: [guard][runs...][guard][ColorARGB32...] per column
+ *   bounds    runCount + 1 records {world-Y of the boundary above run i, RLEElement i} per non-empty column, top to bottom
+ *             (valid when cvxd_world.regular; see world_transcode.h) */
 struct cvxd_lod {
     const uint4* headers;
     const uint32_t* elements;
+    const uint2* bounds;
     int32_t mul_x;      /* dimZ >> lod, World.cs:31 */
     int32_t lod;
 };
@@ -30,6 +32,7 @@ struct cvxd_world {
     cvxd_lod lods[CVXD_LODS];
     int32_t dim_x, dim_y, dim_z;
     int32_t lod_count;
+    int32_t regular;    /* every uploaded LOD consists of full-height columns of valid runs: `bounds` may be used */
 };
 
 /* DrawSegmentRayJob.SegmentContext (Assets/Code/Rendering/DrawSegmentRayJob.cs:718-727) minus the pointers. */
@@ -86,6 +89,5 @@ struct cvxd_ray_state { /* mirrors cvx_ray_state */
 cudaError_t cvxd_launch_phase1(const cvxd_world& world, const cvxd_frame& frame, int group_size, cudaStream_t stream);
 cudaError_t cvxd_launch_phase2(const cvxd_blit& blit, cudaStream_t stream);
 cudaError_t cvxd_launch_ray_setup(const cvxd_world& world, const cvxd_frame& frame, cvxd_ray_state* out, int n, cudaStream_t stream);
-cudaError_t cvxd_launch_transcode_headers(const uint8_t* blob_headers12, uint4* out, const uint32_t* elements, int64_t n_columns, cudaStream_t stream);
 cudaError_t cvxd_launch_fill(uint32_t* dst, uint32_t value, int64_t n, cudaStream_t stream);
 #endif

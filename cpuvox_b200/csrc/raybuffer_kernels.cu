@@ -21,7 +21,11 @@
  *    of :220-221 must survive), same operation order as the reference expressions, so rows match the CPU restatement
  *    bit for bit.
  */
+#ifdef CVX_EMU /* test-only CPU build of this source under tools/simt_emu (never part of the product library) */
+#include "cuda_emu.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <limits.h>
 #include <stdint.h>
 #include "device_types.h"
@@ -332,8 +336,12 @@ struct Acc { unsigned long long dda_steps, columns_nonempty, runs_visited, px_vo
 
 // Load whose result is never used: pulls the line into L1/L2 ahead of the dependent loads of the column body.
 __device__ __forceinline__ void touch(const uint32_t* p) {
+#ifdef CVX_EMU
+    (void)p;
+#else
     uint32_t sink;
     asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(sink) : "l"(p));
+#endif
 }
 
 /*
@@ -353,7 +361,11 @@ __device__ __forceinline__ void touch(const uint32_t* p) {
 template <int G, bool COUNTERS, bool TIMING>
 __global__ void __launch_bounds__(CVXD_THREADS_PER_CTA, CVXD_MIN_CTAS_PER_SM)
 phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ cvxd_frame f) {
+#ifdef CVX_EMU
+    uint32_t* seen_all = emu::g_shared;
+#else
     extern __shared__ uint32_t seen_all[];
+#endif
     constexpr int GROUPS_PER_CTA = CVXD_THREADS_PER_CTA / G;
     constexpr uint32_t GBITS = G == 32 ? FULL_MASK : ((1u << (G & 31)) - 1u);
     const int lane = threadIdx.x & 31;
@@ -904,16 +916,6 @@ __global__ void ray_setup_kernel(const __grid_constant__ cvxd_world world, const
     out[i] = o;
 }
 
-// 12-byte RLEColumn {int offset; ushort runCount, worldMin, worldMax; pad} -> uint4 device header
-__global__ void transcode_headers_kernel(const uint32_t* __restrict__ src12, uint4* __restrict__ dst, const uint32_t* __restrict__ elements, int64_t n) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t w0 = src12[3 * i], w1 = src12[3 * i + 1], w2 = src12[3 * i + 2];
-    uint32_t runCount = w1 & 0xffffu;
-    uint32_t first = runCount ? elements[(int64_t)(int32_t)w0 + 1] : 0u;
-    dst[i] = make_uint4(w0, w1, w2 & 0xffffu, first);
-}
-
 __global__ void fill_kernel(uint32_t* dst, uint32_t value, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -922,6 +924,7 @@ __global__ void fill_kernel(uint32_t* dst, uint32_t value, int64_t n) {
 
 } // namespace
 
+#ifndef CVX_EMU
 template <int G>
 static cudaError_t launch_phase1_g(const cvxd_world& world, const cvxd_frame& frame, int n, cudaStream_t stream) {
     constexpr int groupsPerCta = CVXD_THREADS_PER_CTA / G;
@@ -964,14 +967,9 @@ cudaError_t cvxd_launch_ray_setup(const cvxd_world& world, const cvxd_frame& fra
     return cudaGetLastError();
 }
 
-cudaError_t cvxd_launch_transcode_headers(const uint8_t* blob_headers12, uint4* out, const uint32_t* elements, int64_t n_columns, cudaStream_t stream) {
-    if (n_columns <= 0) return cudaSuccess;
-    transcode_headers_kernel<<<(unsigned)((n_columns + 255) / 256), 256, 0, stream>>>((const uint32_t*)blob_headers12, out, elements, n_columns);
-    return cudaGetLastError();
-}
-
 cudaError_t cvxd_launch_fill(uint32_t* dst, uint32_t value, int64_t n, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
     fill_kernel<<<148 * 8, 256, 0, stream>>>(dst, value, n);
     return cudaGetLastError();
 }
+#endif /* !CVX_EMU */
