@@ -48,6 +48,7 @@ struct cvx_ctx {
     std::vector<cudaEvent_t> profEvents; // 3 per profiled view: start, mid, end
     int profCapacity = 0, profCount = 0;
     int groupSize = 0;                  // lanes per ray in phase 1: 0 = auto, 8, 16, 32
+    int generalPath = 0;                // 1 = never use the boundary-table kernel
     std::string error;
 };
 
@@ -87,6 +88,7 @@ void make_frame(cvx_ctx* ctx, const cvx_frame_setup* s, cvxd_frame& f) {
     cvxh::frame_from_setup(s, ctx->width, ctx->height, f);
     f.td = ctx->td; f.lr = ctx->lr;
     f.counters = (ctx->flags & CVX_FLAG_COUNTERS) ? ctx->counters : nullptr;
+    f.general_path = ctx->generalPath;
 }
 
 void make_blit(cvx_ctx* ctx, const cvxd_frame& f, uint32_t* target, cvxd_blit& b) {
@@ -479,6 +481,11 @@ int cvx_last_draw_ms(cvx_ctx* ctx, float* out_phase1_ms, float* out_phase2_ms) {
 
 int64_t cvx_launch_count(const cvx_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int cvx_world_is_regular(const cvx_ctx* ctx) {
+    if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
+    return ctx->world.lod_count > 0 && ctx->world.regular ? 1 : 0;
+}
+
 int cvx_set_option(cvx_ctx* ctx, int32_t option, int32_t value) {
     if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
     switch (option) {
@@ -488,6 +495,9 @@ int cvx_set_option(cvx_ctx* ctx, int32_t option, int32_t value) {
         return CVX_OK;
     case CVX_OPT_COUNTERS:
         ctx->flags = value ? (ctx->flags | CVX_FLAG_COUNTERS) : (ctx->flags & ~CVX_FLAG_COUNTERS);
+        return CVX_OK;
+    case CVX_OPT_GENERAL_PATH:
+        ctx->generalPath = value ? 1 : 0;
         return CVX_OK;
     default:
         return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "unknown option %d", option);

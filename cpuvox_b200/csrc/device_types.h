@@ -65,6 +65,7 @@ struct cvxd_frame {
     uint32_t* lr;                   /* left/right raybuffer: rows of `width` pixels */
     cvxd_counters* counters;        /* may be null */
     long long* timing;              /* debug: CVXD_TIMING_REGIONS cycle counts per flat ray, or null */
+    int32_t general_path;           /* debug/test: force the general (element-area) kernel even for a regular world */
 };
 
 struct cvxd_blit {

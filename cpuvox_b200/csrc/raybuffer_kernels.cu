@@ -358,7 +358,7 @@ __device__ __forceinline__ void touch(const uint32_t* p) {
 #ifndef CVXD_MIN_CTAS_PER_SM
 #define CVXD_MIN_CTAS_PER_SM 4
 #endif
-template <int G, bool COUNTERS, bool TIMING>
+template <int G, bool COUNTERS, bool TIMING, bool FAST>
 __global__ void __launch_bounds__(CVXD_THREADS_PER_CTA, CVXD_MIN_CTAS_PER_SM)
 phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ cvxd_frame f) {
 #ifdef CVX_EMU
@@ -437,6 +437,9 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
             planeDir = F3{dir[a], dir[2], dir[3]};
         }
         const int maskX = world.dim_x - 1, maskZ = world.dim_z - 1;
+        // unlerp(0, worldMaxY, y) = (y - 0) / (worldMaxY - 0): for a power-of-two height the quotient is exactly y * 2^-k
+        const bool yPow2 = (world.dim_y & (world.dim_y - 1)) == 0;
+        const float invWorldMaxY = 1.0f / worldMaxY;
 
         // Side-span pixels are a colour gather followed by a store: the store is deferred until this lane's next gather (or the end
         // of the ray), so the gather's latency is not on the ray's critical path. Nothing in this kernel reads the row back.
@@ -506,7 +509,10 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
             if (gl < n) hdr = __ldg(world.lods[myLod].headers + myIdx);
             const bool myNonEmpty = (hdr.y & 0xffffu) != 0u;
             // start fetching the run list of every non-empty column of the batch now; the column bodies below find it cached
-            if (myNonEmpty) touch(world.lods[myLod].elements + hdr.x + (ITER > 0 ? 1u : (hdr.y & 0xffffu)));
+            if (myNonEmpty) {
+                if (FAST) touch((const uint32_t*)(world.lods[myLod].bounds + hdr.w + (ITER > 0 ? 0u : (hdr.y & 0xffffu))));
+                else touch(world.lods[myLod].elements + hdr.x + (ITER > 0 ? 1u : (hdr.y & 0xffffu)));
+            }
             const float myWorldMin = (float)(hdr.y >> 16), myWorldMax = (float)(hdr.z & 0xffffu);
             uint32_t remaining = GBALLOT(myNonEmpty);
             int cellsDone = n + (endKind == 1 ? 1 : 0); // the out-of-world probe counts as a step
@@ -521,6 +527,9 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
             int r_ci = 0, r_sMin = 0, r_sMax = 0, r_cMin = 0, r_cMax = 0, r_capKind = 0;
             bool r_sideClip = false, r_capClip = false;
             float r_eMin = 0.0f, r_eMax = 0.0f;
+            // FAST rounds: one BOUNDARY per lane (see world_transcode.h); the lane also owns the run between its boundary and the
+            // next lane's. Kept for the commit: the run's length, its cap colour and the boundary's point on the last line.
+            int r_len = 0; uint32_t r_capColor = 0u; float bFx = 0.0f, bFy = 0.0f, bFz = 0.0f;
             const int myRunCount = (int)(hdr.y & 0xffffu);
 
             // Product builds (no counters): screen-axis hull of this lane's column — the projections of its solid extent
@@ -646,12 +655,12 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                 // ---- runs of this column (:424-611). A column of at most G runs is resolved from the round cache in one pass; a
                 // taller one goes through the same code G runs at a time (k0 = first run of the pass, yDone = world-Y extent of the
                 // runs before it, in LOD voxels times the LOD scale).
-                const bool tall = runCount > G;
+                const bool tall = FAST ? runCount >= G : runCount > G; // FAST: runCount + 1 boundaries must fit the G lanes
                 int k0 = 0, yDone = 0;
                 bool colStop = false;
                 do {
                     STAMP(4);
-                    const int runsHere = tall ? (runCount - k0 < G ? runCount - k0 : G) : runCount;
+                    const int runsHere = tall ? (FAST ? (runCount - k0 < G - 1 ? runCount - k0 : G - 1) : (runCount - k0 < G ? runCount - k0 : G)) : runCount;
                     if (tall || !((roundCols >> c) & 1u)) {
                         // ---- form a round: this column (pass) plus, if it is not a tall one, the following columns that are likely
                         // to be entered, as long as their runs fit in the G lanes. One run per lane: fetch, world-Y bounds (segmented
@@ -665,7 +674,9 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                             follow &= GBALLOT(myNonEmpty && !(myWorldMin > newMax || myWorldMax < newMin));
                         }
                         const uint32_t consider = (1u << c) | follow;
-                        const int v = gl == c ? runsHere : (((consider >> gl) & 1u) ? myRunCount : 0);
+                        // lanes a column needs: one per run, or (FAST) one per boundary = runs + 1; a pass of a tall column takes G
+                        // boundaries, the last of which opens the next pass
+                        const int v = gl == c ? runsHere + (FAST ? 1 : 0) : (((consider >> gl) & 1u) ? myRunCount + (FAST ? 1 : 0) : 0);
                         int incl = v;
 #pragma unroll
                         for (int o = 1; o < G; o <<= 1) { int t = __shfl_up_sync(gmask, incl, o, G); if (gl >= o) incl += t; }
@@ -685,69 +696,162 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                         const uint32_t colOff = GSHFL(hdr.x, myCol);
                         const int colRuns = GSHFL(myRunCount, myCol);
                         const uint32_t* colElems = world.lods[cLod].elements + colOff; // one LOD per batch
-                        uint32_t el = 0u;
-                        if (hasRun) el = __ldg(colElems + (ITER > 0 ? 1 + k : colRuns - k));
-                        r_ci = (int)(short)(el & 0xffffu); const int r_len = (int)(short)(el >> 16); // RLEElement World.cs:245-259
-                        roundInvalid = GBALLOT(hasRun && r_len == 0);  // an invalid element (Length == 0) ends its column (:445-447)
-                        // lanes of my column from its start up to me, and whether an invalid element precedes me there
-                        const uint32_t mineUpToMe = ((2u << gl) - 1u) & ~((1u << myStart) - 1u);
-                        const bool valid = hasRun && !(roundInvalid & mineUpToMe);
-                        const int span = valid ? r_len * cScale : 0;
-                        int sum = span;
-#pragma unroll
-                        for (int o = 1; o < G; o <<= 1) { int t = __shfl_up_sync(gmask, sum, o, G); if (gl >= o) sum += t; }
-                        const int before = GSHFL(sum, myStart > 0 ? myStart - 1 : 0);
-                        const int inclCol = sum - (myStart > 0 ? before : 0) + (myCol == c ? yDone : 0); // my column's runs up to and including me
-                        if (tall) yDone = GSHFL(inclCol, runsHere - 1);                // extent after this pass (the round holds only this column)
-                        if (ITER > 0) { r_eMax = (float)(world.dim_y - (inclCol - span)); r_eMin = (float)(world.dim_y - inclCol); } // :449-455
-                        else          { r_eMin = (float)(inclCol - span); r_eMax = (float)inclCol; }
+                        if (FAST) {
+                            // ---- one boundary per lane: record k of the column (from the top, or from the bottom when iterating
+                            // upwards) = {world-Y of the boundary, RLEElement below it}. The run of lane i lies between the boundaries
+                            // of lanes i and i + 1 (:449-455 without the running sums), and each boundary is projected ONCE on the
+                            // last line (an end of two side spans, :478-502) and once on the next line (an end of one cap span, :554-578).
+                            const uint32_t colB = GSHFL(hdr.w, myCol);
+                            uint2 rec = make_uint2(0u, 0u);
+                            if (hasRun) rec = __ldg(world.lods[cLod].bounds + colB + (ITER > 0 ? k : colRuns - k));
+                            const int yB = (int)rec.x;
+                            const int nextY = __shfl_down_sync(gmask, yB, 1, G);
+                            const uint32_t nextEl = __shfl_down_sync(gmask, rec.y, 1, G);
+                            const bool laneRun = hasRun && k < colRuns && gl + 1 < totalRuns; // a boundary lane followed by the run's other boundary
+                            const uint32_t el = laneRun ? (ITER > 0 ? rec.y : nextEl) : 0x0000ffffu; // others: air of length 0, never solid
+                            r_ci = (int)(short)(el & 0xffffu); r_len = (int)(short)(el >> 16);           // RLEElement World.cs:245-259
+                            if (ITER > 0) { r_eMax = (float)yB; r_eMin = (float)nextY; } else { r_eMin = (float)yB; r_eMax = (float)nextY; }
 
-                        STAMP(5);
-                        const F3 lMinLast = F3{planeBottom.x + planeDir.x * cDl, planeBottom.y + planeDir.y * cDl, planeBottom.z + planeDir.z * cDl}; // :289-293
-                        const F3 lMinNext = F3{planeBottom.x + planeDir.x * cDn, planeBottom.y + planeDir.y * cDn, planeBottom.z + planeDir.z * cDn};
-                        const F3 lMaxLast = F3{planeTop.x + planeDir.x * cDl, planeTop.y + planeDir.y * cDl, planeTop.z + planeDir.z * cDl};
-                        const F3 lMaxNext = F3{planeTop.x + planeDir.x * cDn, planeTop.y + planeDir.y * cDn, planeTop.z + planeDir.z * cDn};
-                        r_sideClip = false; r_capClip = false; r_capKind = 0;
-                        {
-                            float bfx = 0.0f, bfy = 0.0f, uvAx = 0.0f, uvAy = 0.0f, uvBx = 0.0f, uvBy = 0.0f;
-                            int capIdx = 0;
-                            const float portionBottom = unlerpf(0.0f, worldMaxY, r_eMin); // :478-481
-                            const float portionTop = unlerpf(0.0f, worldMaxY, r_eMax);
-                            F3 frontBottom = lerp3(lMinLast, lMaxLast, portionBottom);
-                            F3 frontTop = lerp3(lMinLast, lMaxLast, portionTop);
-                            // which cap, if any, depends on the camera height only (:549,556); its flat colour (:553,560) is fetched
-                            // now, while the divisions below run, and parked in the cache
-                            if (portionTop < cameraPosYNormalized) { r_capKind = 1; capIdx = r_ci; }
-                            else if (portionBottom > cameraPosYNormalized) { r_capKind = 2; capIdx = r_ci + r_len - 1; }
-                            uint32_t capColor = 0u;
-                            if (r_capKind && valid && r_ci >= 0) capColor = __ldg(colElems + colRuns + 2 + capIdx);
-                            float uA = (float)r_len, uB = 0.0f;
-                            if (clip_near_u(frontBottom, frontTop, uA, uB)) { // :489-502 (clips frontBottom/Top in place)
-                                uvAx = 1.0f / frontBottom.z; uvAy = uA / frontBottom.z;
-                                uvBx = 1.0f / frontTop.z;    uvBy = uB / frontTop.z;
-                                bfx = frontBottom.x / frontBottom.z; bfy = frontTop.x / frontTop.z;
-                                if (bfx > bfy) {
-                                    float t = bfx; bfx = bfy; bfy = t;
-                                    t = uvAx; uvAx = uvBx; uvBx = t;
-                                    t = uvAy; uvAy = uvBy; uvBy = t;
-                                }
-                                r_sMin = f2i(rintf(bfx)); r_sMax = f2i(rintf(bfy));
-                                r_sideClip = true;
+                            STAMP(5);
+                            const F3 lMinLast = F3{planeBottom.x + planeDir.x * cDl, planeBottom.y + planeDir.y * cDl, planeBottom.z + planeDir.z * cDl}; // :289-293
+                            const F3 lMinNext = F3{planeBottom.x + planeDir.x * cDn, planeBottom.y + planeDir.y * cDn, planeBottom.z + planeDir.z * cDn};
+                            const F3 lMaxLast = F3{planeTop.x + planeDir.x * cDl, planeTop.y + planeDir.y * cDl, planeTop.z + planeDir.z * cDl};
+                            const F3 lMaxNext = F3{planeTop.x + planeDir.x * cDn, planeTop.y + planeDir.y * cDn, planeTop.z + planeDir.z * cDn};
+                            const float portion = yPow2 ? (float)yB * invWorldMaxY : unlerpf(0.0f, worldMaxY, (float)yB); // :478-479
+                            const F3 Fp = lerp3(lMinLast, lMaxLast, portion), Np = lerp3(lMinNext, lMaxNext, portion);
+                            bFx = Fp.x; bFy = Fp.y; bFz = Fp.z;
+                            const bool fFront = !(Fp.y <= 0.0f), nFront = !(Np.y <= 0.0f); // in front of the near plane (CameraData.cs:126,143)
+                            // which run's cap ends on this boundary: the run below it when it is seen from above (:549), the run above it
+                            // when seen from below (:556); a run takes the first of the two that applies
+                            const int bKind = portion < cameraPosYNormalized ? 1 : (portion > cameraPosYNormalized ? 2 : 0);
+                            const float fpx = Fp.x / Fp.z;
+                            const int fr = f2i(rintf(fpx));
+                            int bcMin = 0, bcMax = 0;
+                            if (bKind && fFront && nFront) { // :571-578
+                                const int nr = f2i(rintf(Np.x / Np.z));
+                                bcMin = nr; bcMax = fr;
+                                if (bcMin > bcMax) { bcMin = fr; bcMax = nr; }
                             }
-                            if (r_capKind) { // :554-578
-                                const float portion = r_capKind == 1 ? portionTop : portionBottom;
-                                F3 secA = lerp3(lMinNext, lMaxNext, portion), secB = r_capKind == 1 ? frontTop : frontBottom;
-                                if (clip_near(secA, secB)) {
-                                    r_cMin = f2i(rintf(secA.x / secA.z)); r_cMax = f2i(rintf(secB.x / secB.z));
-                                    if (r_cMin > r_cMax) { int t = r_cMin; r_cMin = r_cMax; r_cMax = t; }
-                                    r_capClip = true;
+                            const int flags = (fFront ? 1 : 0) | (nFront ? 2 : 0) | (bKind << 2);
+                            const float nextFpx = __shfl_down_sync(gmask, fpx, 1, G);
+                            const int nextFlags = __shfl_down_sync(gmask, flags, 1, G);
+                            const int nextCMin = __shfl_down_sync(gmask, bcMin, 1, G), nextCMax = __shfl_down_sync(gmask, bcMax, 1, G);
+                            const bool nextFront = nextFlags & 1;
+                            const int topKind = ITER > 0 ? bKind : (nextFlags >> 2), botKind = ITER > 0 ? (nextFlags >> 2) : bKind;
+                            r_capKind = topKind == 1 ? 1 : (botKind == 2 ? 2 : 0); // :549,556
+                            const bool capOwn = (r_capKind == 1) == (ITER > 0);      // the cap's boundary is this lane's (else the next lane's)
+                            const bool capNFront = capOwn ? nFront : ((nextFlags & 2) != 0);
+                            r_sideClip = false; r_capClip = false;
+                            const bool solidRun = laneRun && r_ci >= 0;
+                            bool needExact = false;
+                            if (solidRun) {
+                                if (fFront && nextFront) {
+                                    // both ends in front of the near plane: ClipHomogeneousCameraSpaceLine changes nothing
+                                    const float fb = ITER > 0 ? nextFpx : fpx, ft = ITER > 0 ? fpx : nextFpx; // bottom / top end
+                                    const int nextFr = f2i(rintf(nextFpx));
+                                    const int rb = ITER > 0 ? nextFr : fr, rt = ITER > 0 ? fr : nextFr;
+                                    if (fb > ft) { r_sMin = rt; r_sMax = rb; } else { r_sMin = rb; r_sMax = rt; } // :496-502
+                                    r_sideClip = true;
+                                    if (r_capKind) {
+                                        if (capNFront) { r_cMin = capOwn ? bcMin : nextCMin; r_cMax = capOwn ? bcMax : nextCMax; r_capClip = true; }
+                                        else needExact = true;
+                                    }
+                                } else if (!fFront && !nextFront) {
+                                    // both ends behind: no side span; the cap's last-line end is behind too, so the cap exists only if its
+                                    // next-line end is in front (and then it is clipped)
+                                    if (r_capKind && capNFront) needExact = true;
+                                } else needExact = true;
+                                if (r_capKind) r_capColor = __ldg(colElems + colRuns + 2 + (r_capKind == 1 ? r_ci : r_ci + r_len - 1)); // :553,560
+                            }
+                            if (GBALLOT(needExact)) {
+                                // ---- a run straddles the near plane: the reference's per-run clipping (rare; columns next to the camera)
+                                const F3 nF = F3{__shfl_down_sync(gmask, Fp.x, 1, G), __shfl_down_sync(gmask, Fp.y, 1, G), __shfl_down_sync(gmask, Fp.z, 1, G)};
+                                const F3 nN = F3{__shfl_down_sync(gmask, Np.x, 1, G), __shfl_down_sync(gmask, Np.y, 1, G), __shfl_down_sync(gmask, Np.z, 1, G)};
+                                if (needExact) {
+                                    F3 frontBottom = ITER > 0 ? nF : Fp, frontTop = ITER > 0 ? Fp : nF;
+                                    float uA = (float)r_len, uB = 0.0f;
+                                    r_sideClip = false; r_capClip = false;
+                                    if (clip_near_u(frontBottom, frontTop, uA, uB)) { // :489-502 (clips frontBottom/Top in place)
+                                        float bfx = frontBottom.x / frontBottom.z, bfy = frontTop.x / frontTop.z;
+                                        if (bfx > bfy) { float t = bfx; bfx = bfy; bfy = t; }
+                                        r_sMin = f2i(rintf(bfx)); r_sMax = f2i(rintf(bfy));
+                                        r_sideClip = true;
+                                    }
+                                    if (r_capKind) { // :554-578
+                                        F3 secA = capOwn ? Np : nN, secB = r_capKind == 1 ? frontTop : frontBottom;
+                                        if (clip_near(secA, secB)) {
+                                            r_cMin = f2i(rintf(secA.x / secA.z)); r_cMax = f2i(rintf(secB.x / secB.z));
+                                            if (r_cMin > r_cMax) { int t = r_cMin; r_cMin = r_cMax; r_cMax = t; }
+                                            r_capClip = true;
+                                        }
+                                    }
                                 }
                             }
-                            cache[0 * G + gl] = __float_as_uint(bfx);  cache[1 * G + gl] = __float_as_uint(bfy);
-                            cache[2 * G + gl] = __float_as_uint(uvAx); cache[3 * G + gl] = __float_as_uint(uvAy);
-                            cache[4 * G + gl] = __float_as_uint(uvBx); cache[5 * G + gl] = __float_as_uint(uvBy);
-                            cache[6 * G + gl] = (uint32_t)r_len;       cache[7 * G + gl] = capColor;
-                            __syncwarp(gmask);
+                        } else {
+                            uint32_t el = 0u;
+                            if (hasRun) el = __ldg(colElems + (ITER > 0 ? 1 + k : colRuns - k));
+                            r_ci = (int)(short)(el & 0xffffu); r_len = (int)(short)(el >> 16); // RLEElement World.cs:245-259
+                            roundInvalid = GBALLOT(hasRun && r_len == 0);  // an invalid element (Length == 0) ends its column (:445-447)
+                            // lanes of my column from its start up to me, and whether an invalid element precedes me there
+                            const uint32_t mineUpToMe = ((2u << gl) - 1u) & ~((1u << myStart) - 1u);
+                            const bool valid = hasRun && !(roundInvalid & mineUpToMe);
+                            const int span = valid ? r_len * cScale : 0;
+                            int sum = span;
+    #pragma unroll
+                            for (int o = 1; o < G; o <<= 1) { int t = __shfl_up_sync(gmask, sum, o, G); if (gl >= o) sum += t; }
+                            const int before = GSHFL(sum, myStart > 0 ? myStart - 1 : 0);
+                            const int inclCol = sum - (myStart > 0 ? before : 0) + (myCol == c ? yDone : 0); // my column's runs up to and including me
+                            if (tall) yDone = GSHFL(inclCol, runsHere - 1);                // extent after this pass (the round holds only this column)
+                            if (ITER > 0) { r_eMax = (float)(world.dim_y - (inclCol - span)); r_eMin = (float)(world.dim_y - inclCol); } // :449-455
+                            else          { r_eMin = (float)(inclCol - span); r_eMax = (float)inclCol; }
+
+                            STAMP(5);
+                            const F3 lMinLast = F3{planeBottom.x + planeDir.x * cDl, planeBottom.y + planeDir.y * cDl, planeBottom.z + planeDir.z * cDl}; // :289-293
+                            const F3 lMinNext = F3{planeBottom.x + planeDir.x * cDn, planeBottom.y + planeDir.y * cDn, planeBottom.z + planeDir.z * cDn};
+                            const F3 lMaxLast = F3{planeTop.x + planeDir.x * cDl, planeTop.y + planeDir.y * cDl, planeTop.z + planeDir.z * cDl};
+                            const F3 lMaxNext = F3{planeTop.x + planeDir.x * cDn, planeTop.y + planeDir.y * cDn, planeTop.z + planeDir.z * cDn};
+                            r_sideClip = false; r_capClip = false; r_capKind = 0;
+                            {
+                                float bfx = 0.0f, bfy = 0.0f, uvAx = 0.0f, uvAy = 0.0f, uvBx = 0.0f, uvBy = 0.0f;
+                                int capIdx = 0;
+                                const float portionBottom = unlerpf(0.0f, worldMaxY, r_eMin); // :478-481
+                                const float portionTop = unlerpf(0.0f, worldMaxY, r_eMax);
+                                F3 frontBottom = lerp3(lMinLast, lMaxLast, portionBottom);
+                                F3 frontTop = lerp3(lMinLast, lMaxLast, portionTop);
+                                // which cap, if any, depends on the camera height only (:549,556); its flat colour (:553,560) is fetched
+                                // now, while the divisions below run, and parked in the cache
+                                if (portionTop < cameraPosYNormalized) { r_capKind = 1; capIdx = r_ci; }
+                                else if (portionBottom > cameraPosYNormalized) { r_capKind = 2; capIdx = r_ci + r_len - 1; }
+                                uint32_t capColor = 0u;
+                                if (r_capKind && valid && r_ci >= 0) capColor = __ldg(colElems + colRuns + 2 + capIdx);
+                                float uA = (float)r_len, uB = 0.0f;
+                                if (clip_near_u(frontBottom, frontTop, uA, uB)) { // :489-502 (clips frontBottom/Top in place)
+                                    uvAx = 1.0f / frontBottom.z; uvAy = uA / frontBottom.z;
+                                    uvBx = 1.0f / frontTop.z;    uvBy = uB / frontTop.z;
+                                    bfx = frontBottom.x / frontBottom.z; bfy = frontTop.x / frontTop.z;
+                                    if (bfx > bfy) {
+                                        float t = bfx; bfx = bfy; bfy = t;
+                                        t = uvAx; uvAx = uvBx; uvBx = t;
+                                        t = uvAy; uvAy = uvBy; uvBy = t;
+                                    }
+                                    r_sMin = f2i(rintf(bfx)); r_sMax = f2i(rintf(bfy));
+                                    r_sideClip = true;
+                                }
+                                if (r_capKind) { // :554-578
+                                    const float portion = r_capKind == 1 ? portionTop : portionBottom;
+                                    F3 secA = lerp3(lMinNext, lMaxNext, portion), secB = r_capKind == 1 ? frontTop : frontBottom;
+                                    if (clip_near(secA, secB)) {
+                                        r_cMin = f2i(rintf(secA.x / secA.z)); r_cMax = f2i(rintf(secB.x / secB.z));
+                                        if (r_cMin > r_cMax) { int t = r_cMin; r_cMin = r_cMax; r_cMax = t; }
+                                        r_capClip = true;
+                                    }
+                                }
+                                cache[0 * G + gl] = __float_as_uint(bfx);  cache[1 * G + gl] = __float_as_uint(bfy);
+                                cache[2 * G + gl] = __float_as_uint(uvAx); cache[3 * G + gl] = __float_as_uint(uvAy);
+                                cache[4 * G + gl] = __float_as_uint(uvBx); cache[5 * G + gl] = __float_as_uint(uvBy);
+                                cache[6 * G + gl] = (uint32_t)r_len;       cache[7 * G + gl] = capColor;
+                                __syncwarp(gmask);
+                            }
                         }
                         STAMP(4);
                     }
@@ -787,20 +891,48 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                         int bMin = GSHFL(isCap ? r_cMin : r_sMin, j), bMax = GSHFL(isCap ? r_cMax : r_sMax, j);
                         reduce_pixel_horizon(rw, bMin, bMax); // :507-517 / :583-593
                         if (isCap) {
-                            const uint32_t color = cache[7 * G + j];
+                            const uint32_t color = FAST ? GSHFL(r_capColor, j) : cache[7 * G + j];
                             for (int y = bMin + gl; y <= bMax; y += G) // :595-602
                                 if (!((rw.seen[y >> 5] >> (y & 31)) & 1u)) row[y] = color;
                         } else {
-                            const float jbfx = __uint_as_float(cache[0 * G + j]), jbfy = __uint_as_float(cache[1 * G + j]);
-                            const float jAx = __uint_as_float(cache[2 * G + j]), jAy = __uint_as_float(cache[3 * G + j]);
-                            const float jBx = __uint_as_float(cache[4 * G + j]), jBy = __uint_as_float(cache[5 * G + j]);
-                            const int jLen = (int)cache[6 * G + j], jCi = GSHFL(r_ci, j);
+                            float jbfx, jbfy, jAx, jAy, jBx, jBy;
+                            int jLen;
+                            const int jCi = GSHFL(r_ci, j);
+                            if (FAST) {
+                                // the perspective-correct u of :490-491,525-530 is needed only now, for the one span that writes, and
+                                // only if the run is longer than one voxel (clamp(floor(u), 0, Length - 1) is 0 otherwise): rebuild the
+                                // span's ends from the boundary points of lanes j and j + 1 exactly as :478-502 does
+                                jLen = GSHFL(r_len, j);
+                                jbfx = jbfy = jAx = jAy = jBx = jBy = 0.0f;
+                                if (jLen > 1) {
+                                    const F3 pj = F3{GSHFL(bFx, j), GSHFL(bFy, j), GSHFL(bFz, j)}, pn = F3{GSHFL(bFx, j + 1), GSHFL(bFy, j + 1), GSHFL(bFz, j + 1)};
+                                    F3 frontBottom = ITER > 0 ? pn : pj, frontTop = ITER > 0 ? pj : pn;
+                                    float uA = (float)jLen, uB = 0.0f;
+                                    clip_near_u(frontBottom, frontTop, uA, uB);
+                                    jAx = 1.0f / frontBottom.z; jAy = uA / frontBottom.z;
+                                    jBx = 1.0f / frontTop.z;    jBy = uB / frontTop.z;
+                                    jbfx = frontBottom.x / frontBottom.z; jbfy = frontTop.x / frontTop.z;
+                                    if (jbfx > jbfy) {
+                                        float t = jbfx; jbfx = jbfy; jbfy = t;
+                                        t = jAx; jAx = jBx; jBx = t;
+                                        t = jAy; jAy = jBy; jBy = t;
+                                    }
+                                }
+                            } else {
+                                jbfx = __uint_as_float(cache[0 * G + j]); jbfy = __uint_as_float(cache[1 * G + j]);
+                                jAx = __uint_as_float(cache[2 * G + j]); jAy = __uint_as_float(cache[3 * G + j]);
+                                jBx = __uint_as_float(cache[4 * G + j]); jBy = __uint_as_float(cache[5 * G + j]);
+                                jLen = (int)cache[6 * G + j];
+                            }
                             for (int y = bMin + gl; y <= bMax; y += G) { // :519-533
                                 if (!((rw.seen[y >> 5] >> (y & 31)) & 1u)) {
-                                    float l = unlerpf(jbfx, jbfy, (float)y);
-                                    float wx = lerpf(jAx, jBx, l), wy = lerpf(jAy, jBy, l);
-                                    float u = wy / wx;
-                                    int idx = max(0, min(jLen - 1, f2i(floorf(u)))) + jCi;
+                                    int idx = jCi;
+                                    if (!FAST || jLen > 1) {
+                                        float l = unlerpf(jbfx, jbfy, (float)y);
+                                        float wx = lerpf(jAx, jBx, l), wy = lerpf(jAy, jBy, l);
+                                        float u = wy / wx;
+                                        idx = max(0, min(jLen - 1, f2i(floorf(u)))) + jCi;
+                                    }
                                     if (pendY >= 0) row[pendY] = pendColor; // the gather issued by the previous commit has long arrived
                                     pendColor = __ldg(colColors + idx); pendY = y;
                                 }
@@ -813,7 +945,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                         if (rw.nf_min > rw.nf_max) { terminated = true; visitedHere = j + 1 - base; break; } // :535-539,604-608
                     }
                     if (COUNTERS && gl == 0) acc.runs_visited += visitedHere;
-                    if (tall) { k0 += G; roundCols = 0u; } // the cache held one pass of this column only
+                    if (tall) { k0 += FAST ? G - 1 : G; roundCols = 0u; } // the cache held one pass of this column only
                 } while (tall && k0 < runCount && !colStop && !terminated);
                 STAMP(4);
                 if (terminated) { cellsDone = c + 1; break; }
@@ -931,12 +1063,20 @@ static cudaError_t launch_phase1_g(const cvxd_world& world, const cvxd_frame& fr
     const int blocks = (n + groupsPerCta - 1) / groupsPerCta;
     const int seenWords = ((frame.width > frame.height ? frame.width : frame.height) + 31) >> 5;
     const size_t smem = (size_t)groupsPerCta * (seenWords + ((seenWords + 31) >> 5) + 9 * G) * sizeof(uint32_t);
+    // FAST: the boundary-table kernel, for regular worlds (world_transcode.h) at the full-warp group width
+    const bool fast = G == 32 && world.regular && !frame.general_path;
     if (frame.timing) {
-        if (G == 32) phase1_kernel<32, false, true><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
-        else return cudaErrorInvalidValue; // the timing build exists for the default group width only
+        if (G != 32) return cudaErrorInvalidValue; // the timing build exists for the default group width only
+        if (fast) phase1_kernel<32, false, true, true><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
+        else      phase1_kernel<32, false, true, false><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
     }
-    else if (frame.counters) phase1_kernel<G, true, false><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
-    else                     phase1_kernel<G, false, false><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
+    else if (frame.counters) {
+        if (fast) phase1_kernel<32, true, false, true><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
+        else      phase1_kernel<G, true, false, false><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
+    } else {
+        if (fast) phase1_kernel<32, false, false, true><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
+        else      phase1_kernel<G, false, false, false><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
+    }
     return cudaGetLastError();
 }
 

@@ -286,6 +286,15 @@ class RenderManager:
     def set_counters(self, on: bool):
         self.set_option(N.OPT_COUNTERS, int(on))
 
+    def set_general_path(self, on: bool):
+        """True = always run the general Phase-1 kernel; False (default) = boundary-table kernel for regular worlds."""
+        self.set_option(N.OPT_GENERAL_PATH, int(on))
+
+    def world_is_regular(self) -> bool:
+        r = lib.cvx_world_is_regular(self._ctx)
+        self._ck(min(r, 0))
+        return bool(r)
+
     def profile_begin(self, max_draws: int):
         self._ck(lib.cvx_profile_begin(self._ctx, max_draws))
 

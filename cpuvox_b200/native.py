@@ -72,6 +72,7 @@ class Config(C.Structure):
 FLAG_COUNTERS = 1
 OPT_GROUP_SIZE = 1
 OPT_COUNTERS = 2
+OPT_GENERAL_PATH = 3
 
 
 class Pose(C.Structure):
@@ -131,6 +132,7 @@ SYMBOLS = {
     "cvx_last_draw_ms": (C.c_int, [_P, C.POINTER(_F), C.POINTER(_F)]),
     "cvx_launch_count": (_I64, [_P]),
     "cvx_set_option": (C.c_int, [_P, _I32, _I32]),
+    "cvx_world_is_regular": (C.c_int, [_P]),
     "cvx_profile_begin": (C.c_int, [_P, _I32]),
     "cvx_profile_end": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I32)]),
     "cvx_ipc_export_frame": (C.c_int, [_P, C.POINTER(C.c_uint8 * 64)]),

@@ -151,10 +151,16 @@ int64_t cvx_launch_count(const cvx_ctx* ctx);
 
 /* Tuning / measurement knobs (no reference analogue).
  *   CVX_OPT_GROUP_SIZE  lanes cooperating on one ray in Phase 1: 0 = choose per frame from the ray count, or 8, 16, 32.
- *   CVX_OPT_COUNTERS    1 = accumulate cvx_counters (same as CVX_FLAG_COUNTERS at creation), 0 = off. */
+ *   CVX_OPT_COUNTERS    1 = accumulate cvx_counters (same as CVX_FLAG_COUNTERS at creation), 0 = off.
+ *   CVX_OPT_GENERAL_PATH 1 = always run the general Phase-1 kernel (reads the reference element area run by run); 0 (default) =
+ *                       use the boundary-table kernel whenever the uploaded world is regular (see cvx_world_is_regular). */
 #define CVX_OPT_GROUP_SIZE 1
 #define CVX_OPT_COUNTERS 2
+#define CVX_OPT_GENERAL_PATH 3
 int cvx_set_option(cvx_ctx* ctx, int32_t option, int32_t value);
+/* 1 when every uploaded LOD consists of full-height columns of valid runs (what WorldBuilder.ToFinalColumn emits,
+ * WordBuilder.cs:232-256): Phase 1 then runs its boundary-table kernel. 0 = the general kernel is used. < 0 = error. */
+int cvx_world_is_regular(const cvx_ctx* ctx);
 /* Device-side timing of many draws: after cvx_profile_begin every cvx_draw / cvx_draw_batch view records CUDA
  * events around Phase 1 and Phase 2 on the context's stream (up to max_draws views); cvx_profile_end waits for
  * them and returns the summed kernel durations in milliseconds and the number of views timed. */

@@ -93,3 +93,56 @@ def pose_for(cv, world, spec, far_scale=2.0):
 def setup_for(cv, world, spec, W, H):
     lods = cv.setup_lods(world.max_dimension, W, H)
     return cv.frame_setup(pose_for(cv, world, spec), W, H, lods, world.dims[1])
+
+
+def comb_world(cv):
+    """Hand-built 64x256x64 world (tests/rle.py encoder): comb columns of 128 one-voxel runs and 8x8 columns of ~70 random voxels
+    (tall columns: several passes of the Phase-1 round cache), plus scattered short runs. Returns (World, blob, column_count)."""
+    from rle import encode_world
+    rng = np.random.default_rng(5)
+    dims = (64, 256, 64)
+    grid = np.zeros(dims, dtype=np.uint32)
+    for (x, z) in [(20, 20), (21, 20), (40, 33), (10, 50), (33, 34)]:
+        grid[x, ::2, z] = rng.integers(1, 2**32 - 1, size=128, dtype=np.uint64).astype(np.uint32) | 0xFF
+    for _ in range(300):
+        x, z = rng.integers(0, 64, 2)
+        y0 = rng.integers(0, 250)
+        h = rng.integers(1, 6)
+        grid[x, y0:y0 + h, z] = rng.integers(1, 2**32 - 1, dtype=np.uint64).astype(np.uint32) | 0xFF
+    for x in range(28, 36):
+        for z in range(28, 36):
+            ys = rng.integers(0, 256, size=70)
+            grid[x, ys, z] = rng.integers(1, 2**32 - 1, size=70, dtype=np.uint64).astype(np.uint32) | 0xFF
+    blob, cc = encode_world(grid)
+    return cv.World(dims, [blob], [cc], [int((grid != 0).sum())]), blob, cc
+
+
+# camera (position, euler) cases for comb_world: from the side, from above, inside the tall block (near-plane clipping of
+# runs that straddle the camera plane), looking up, rolled, high above looking straight down
+COMB_POSES = [((32.5, 128.5, 2.5), (0, 0, 0)), ((32.5, 200.5, 32.5), (80, 10, 0)), ((31.5, 100.3, 31.5), (30, 45, 0)),
+              ((32.2, 40.5, 30.5), (-50, 200, 0)), ((5.5, 250.5, 5.5), (45, 45, 20)), ((32.5, 128.5, 32.5), (5, 90, 0)),
+              ((32.5, 300.5, 32.5), (89, 0, 0))]
+
+
+def irregular_world(cv):
+    """A world whose columns are NOT all full-height runs of valid elements (a zero-length element inside one column, a
+    column that stops short of the floor): the upload must classify it as irregular and Phase 1 must take the general kernel."""
+    from rle import encode_world
+    rng = np.random.default_rng(11)
+    dims = (32, 64, 32)
+    grid = np.zeros(dims, dtype=np.uint32)
+    for _ in range(400):
+        x, z = rng.integers(0, 32, 2)
+        y0 = rng.integers(0, 60)
+        grid[x, y0:y0 + rng.integers(1, 5), z] = rng.integers(1, 2**32 - 1, dtype=np.uint64).astype(np.uint32) | 0xFF
+    blob, cc = encode_world(grid)
+    words = blob.view(np.uint32)
+    cells = words[3 * cc:]
+    hdr = words[:3 * cc].reshape(cc, 3)
+    multi = [i for i in range(32 * 32) if (hdr[i, 1] & 0xFFFF) >= 4]
+    a, b = multi[0], multi[len(multi) // 2]
+    cells[hdr[a, 0] + 3] = cells[hdr[a, 0] + 3] & 0xFFFF          # run 2 of column a: Length 0 -> the reference stops there
+    last = hdr[b, 0] + (hdr[b, 1] & 0xFFFF)
+    e = int(cells[last])
+    cells[last] = (e & 0xFFFF) | ((((e >> 16) & 0xFFFF) + 3) << 16)  # column b: lengths no longer add up to the height
+    return cv.World(dims, [blob], [cc], [int((grid != 0).sum())]), blob, cc

@@ -11,7 +11,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import MILL, POSES, ROOT, crc, pose_for, setup_for
+from conftest import COMB_POSES, MILL, POSES, ROOT, comb_world, crc, irregular_world, pose_for, setup_for
 from rle import encode_world
 
 pytestmark = pytest.mark.gpu
@@ -52,8 +52,17 @@ def _gpu_frame(rm, s, fill):
     rm.sync()
     td2, lr2 = rm.read_raybuffers()
     frame2 = rm.read_frame()
-    rm.set_counters(True)
     assert np.array_equal(td, td2) and np.array_equal(lr, lr2) and np.array_equal(frame, frame2), "product build differs from counter build"
+    if rm.world_is_regular():
+        # the same frame through the general kernel (element area, run by run) instead of the boundary-table kernel
+        rm.set_general_path(True)
+        rm.clear_raybuffers(fill)
+        rm.draw_setup(s)
+        rm.sync()
+        td3, lr3 = rm.read_raybuffers()
+        rm.set_general_path(False)
+        assert np.array_equal(td, td3) and np.array_equal(lr, lr3), "general kernel differs from the boundary-table kernel"
+    rm.set_counters(True)
     return td, lr, cn, frame
 
 
@@ -79,6 +88,7 @@ def test_matches_oracle_all_poses(cv, orc, rm, request, world_name, group):
     world = request.getfixturevalue(world_name)
     ow = orc.OracleWorld(world.dims, world.blobs, world.column_counts)
     rm.upload_world(world)
+    assert rm.world_is_regular(), "builder-made worlds are regular: the boundary-table kernel is the one under test at group 0/32"
     rm.set_group_size(group)
     for (W, H) in RESOLUTIONS:
         rm.set_resolution(W, H)
@@ -210,6 +220,30 @@ def test_hand_made_worlds(cv, orc, rm):
     assert seq == [c_bot, c_mid, c_top]
     ow = orc.OracleWorld(dims, [blob], [cc])
     _assert_same(g, _oracle_frame(orc, ow, s, W, H, 0), "single column")
+
+
+def test_tall_columns_near_plane_and_irregular_worlds(cv, orc, rm):
+    """Columns of 70..128 runs (several round-cache passes), cameras inside geometry (runs straddling the near plane), and a world
+    that is not made of full-height valid runs (must be classified irregular and rendered by the general kernel)."""
+    lods = np.full(6, 1e9, dtype=np.float32)
+    world, blob, cc = comb_world(cv)
+    ow = orc.OracleWorld(world.dims, [blob], [cc])
+    rm.upload_world(world)
+    assert rm.world_is_regular()
+    for (W, H) in [(320, 180), (200, 300)]:
+        rm.set_resolution(W, H)
+        for pos, eul in COMB_POSES:
+            s = cv.frame_setup(cv.CameraPose.from_euler(pos, eul, far_clip=200.0), W, H, lods, world.dims[1])
+            _assert_same(_gpu_frame(rm, s, MAGENTA), _oracle_frame(orc, ow, s, W, H, MAGENTA), f"comb {pos} {eul} {W}x{H}")
+    world, blob, cc = irregular_world(cv)
+    ow = orc.OracleWorld(world.dims, [blob], [cc])
+    rm.upload_world(world)
+    assert not rm.world_is_regular()
+    W, H = 256, 192
+    rm.set_resolution(W, H)
+    for pos, eul in [((16.5, 40.5, 2.5), (10, 0, 0)), ((16.5, 70.5, 16.5), (75, 30, 0)), ((3.5, 20.5, 3.5), (-30, 45, 0))]:
+        s = cv.frame_setup(cv.CameraPose.from_euler(pos, eul, far_clip=100.0), W, H, lods, world.dims[1])
+        _assert_same(_gpu_frame(rm, s, MAGENTA), _oracle_frame(orc, ow, s, W, H, MAGENTA), f"irregular {pos} {eul}")
 
 
 def test_error_paths(cv):

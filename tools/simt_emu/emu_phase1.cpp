@@ -26,13 +26,11 @@ template <int G>
 void body_g(void* p) {
     const LaunchArgs* a = (const LaunchArgs*)p;
     if (a->variant == 0) {
-        if (a->counters) phase1_kernel<G, true, false>(*a->world, *a->frame);
-        else phase1_kernel<G, false, false>(*a->world, *a->frame);
-    } else {
-#ifdef CVX_HAVE_FAST
-        if (a->counters) phase1_fast_kernel<true>(*a->world, *a->frame);
-        else phase1_fast_kernel<false>(*a->world, *a->frame);
-#endif
+        if (a->counters) phase1_kernel<G, true, false, false>(*a->world, *a->frame);
+        else phase1_kernel<G, false, false, false>(*a->world, *a->frame);
+    } else if (G == 32) {
+        if (a->counters) phase1_kernel<32, true, false, true>(*a->world, *a->frame);
+        else phase1_kernel<32, false, false, true>(*a->world, *a->frame);
     }
 }
 
