@@ -530,6 +530,12 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
             // FAST rounds: one BOUNDARY per lane (see world_transcode.h); the lane also owns the run between its boundary and the
             // next lane's. Kept for the commit: the run's length, its cap colour and the boundary's point on the last line.
             int r_len = 0; uint32_t r_capColor = 0u; float bFx = 0.0f, bFy = 0.0f, bFz = 0.0f;
+            // Lanes of the round whose side / cap span held an unwritten pixel of the writable range when the round was formed. Written
+            // pixels only grow and the writable range only shrinks, so these stay SUPERSETS of the spans that can still write: a
+            // cached column none of whose lanes is set is inert (skipped like a culled one, see the hull comment below), and the
+            // commit loop looks at the set lanes only.
+            uint32_t roundHotS = 0u, roundHotC = 0u;
+            bool r_solid = false;         // this lane holds a valid, non-air run
             const int myRunCount = (int)(hdr.y & 0xffffu);
 
             // Product builds (no counters): screen-axis hull of this lane's column — the projections of its solid extent
@@ -566,7 +572,12 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                     const float newMin = camY + frustumDirMinWorld * distBot;
                     const bool outOfWorld = newMin > worldMaxY || newMax < 0.0f;      // frustum left the world: ray ends
                     const bool culled = myWorldMin > newMax || myWorldMax < newMin;   // column outside the writable world bounds
-                    const bool inert = CVXD_HULL && !COUNTERS && !culled && !span_would_write(rw, hullMin, hullMax); // cannot write: no side effects
+                    // cannot write, hence no side effects: exactly known for a column in the round cache, by its hull otherwise
+                    bool inert = false;
+                    if (CVXD_HULL && !COUNTERS && !culled && myNonEmpty) {
+                        if ((roundCols >> gl) & 1u) inert = !((roundHotS | roundHotC) & ((myRunCount >= 32 ? FULL_MASK : ((1u << myRunCount) - 1u)) << myBase));
+                        else inert = !span_would_write(rw, hullMin, hullMax);
+                    }
                     const uint32_t cand = GBALLOT(myNonEmpty && (outOfWorld || !(culled || inert))) & remaining;
                     if (!cand) {
                         if (COUNTERS && gl == 0) acc.columns_nonempty += __popc(remaining);
@@ -743,6 +754,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                             const bool capNFront = capOwn ? nFront : ((nextFlags & 2) != 0);
                             r_sideClip = false; r_capClip = false;
                             const bool solidRun = laneRun && r_ci >= 0;
+                            r_solid = solidRun;
                             bool needExact = false;
                             if (solidRun) {
                                 if (fFront && nextFront) {
@@ -795,6 +807,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                             // lanes of my column from its start up to me, and whether an invalid element precedes me there
                             const uint32_t mineUpToMe = ((2u << gl) - 1u) & ~((1u << myStart) - 1u);
                             const bool valid = hasRun && !(roundInvalid & mineUpToMe);
+                            r_solid = valid && r_ci >= 0;
                             const int span = valid ? r_len * cScale : 0;
                             int sum = span;
     #pragma unroll
@@ -853,6 +866,9 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                                 __syncwarp(gmask);
                             }
                         }
+                        STAMP(6);
+                        roundHotS = GBALLOT(r_solid && r_sideClip && span_would_write(rw, r_sMin, r_sMax));
+                        roundHotC = GBALLOT(r_solid && r_capClip && span_would_write(rw, r_cMin, r_cMax));
                         STAMP(4);
                     }
 
@@ -877,18 +893,15 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                     // ---- commit, in reference order (side of run j, cap of run j, side of run j+1, ...), only the spans that still
                     // hold an unwritten pixel; everything ordered before the committed span is a no-op now and stays one (written
                     // pixels only grow, the writable range only shrinks), so it is retired with it.
-                    uint32_t pendingS = GBALLOT(sideOk), pendingC = GBALLOT(capOk);
+                    uint32_t candS = GBALLOT(sideOk) & roundHotS, candC = GBALLOT(capOk) & roundHotC;
                     int visitedHere = endVisit - base;
-                    while (pendingS | pendingC) {
-                        const uint32_t hotS = GBALLOT(((pendingS >> gl) & 1u) && span_would_write(rw, r_sMin, r_sMax));
-                        const uint32_t hotC = GBALLOT(((pendingC >> gl) & 1u) && span_would_write(rw, r_cMin, r_cMax));
-                        if (!(hotS | hotC)) break;
-                        const int jS = hotS ? __ffs(hotS) - 1 : 64, jC = hotC ? __ffs(hotC) - 1 : 64;
+                    while (candS | candC) {
+                        const int jS = candS ? __ffs(candS) - 1 : 64, jC = candC ? __ffs(candC) - 1 : 64;
                         const bool isCap = jC < jS;
                         const int j = isCap ? jC : jS;
-                        pendingS &= ~((2u << j) - 1u);
-                        pendingC &= isCap ? ~((2u << j) - 1u) : ~((1u << j) - 1u);
+                        if (isCap) candC &= candC - 1u; else candS &= candS - 1u;
                         int bMin = GSHFL(isCap ? r_cMin : r_sMin, j), bMax = GSHFL(isCap ? r_cMax : r_sMax, j);
+                        if (!span_would_write(rw, bMin, bMax)) continue; // written over / cut off since the round was formed
                         reduce_pixel_horizon(rw, bMin, bMax); // :507-517 / :583-593
                         if (isCap) {
                             const uint32_t color = FAST ? GSHFL(r_capColor, j) : cache[7 * G + j];
@@ -1063,18 +1076,18 @@ static cudaError_t launch_phase1_g(const cvxd_world& world, const cvxd_frame& fr
     const int blocks = (n + groupsPerCta - 1) / groupsPerCta;
     const int seenWords = ((frame.width > frame.height ? frame.width : frame.height) + 31) >> 5;
     const size_t smem = (size_t)groupsPerCta * (seenWords + ((seenWords + 31) >> 5) + 9 * G) * sizeof(uint32_t);
-    // FAST: the boundary-table kernel, for regular worlds (world_transcode.h) at the full-warp group width
-    const bool fast = G == 32 && world.regular && !frame.general_path;
+    // FAST: the boundary-table kernel, for regular worlds (world_transcode.h)
+    const bool fast = world.regular && !frame.general_path;
     if (frame.timing) {
         if (G != 32) return cudaErrorInvalidValue; // the timing build exists for the default group width only
         if (fast) phase1_kernel<32, false, true, true><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
         else      phase1_kernel<32, false, true, false><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
     }
     else if (frame.counters) {
-        if (fast) phase1_kernel<32, true, false, true><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
+        if (fast) phase1_kernel<G, true, false, true><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
         else      phase1_kernel<G, true, false, false><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
     } else {
-        if (fast) phase1_kernel<32, false, false, true><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
+        if (fast) phase1_kernel<G, false, false, true><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
         else      phase1_kernel<G, false, false, false><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
     }
     return cudaGetLastError();

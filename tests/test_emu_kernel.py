@@ -18,7 +18,7 @@ def _check(cv, orc, ow, ew, s, W, H, what, variants=(0, 1), groups=(32,)):
     lr0 = np.full((2 * W + H, W), MAGENTA, dtype=np.uint32)
     otd, olr, ocn = orc.render_raybuffers(ow, orc.copy_setup(s), W, H, td=td0, lr=lr0)
     for variant in variants:
-        for group in (groups if variant == 0 else (32,)):
+        for group in groups:
             for counters in (True, False):
                 td, lr, cn = emu.render_raybuffers(ew, s, W, H, variant=variant, group=group, counters=counters, fill=MAGENTA)
                 tag = f"{what} kernel={'general' if variant == 0 else 'boundary-table'} g{group} counters={counters}"
@@ -44,12 +44,12 @@ def test_emulated_kernels_match_oracle(cv, orc, request, world_name, res, poses)
 
 
 def test_emulated_narrow_groups(cv, orc, terrain_world):
-    """8 and 16 lanes per ray (general kernel only)."""
+    """8 and 16 lanes per ray, both kernels."""
     ow = orc.OracleWorld(terrain_world.dims, terrain_world.blobs, terrain_world.column_counts)
     ew = emu.EmuWorld(terrain_world)
     W, H = 96, 64
     for spec in (POSES[0], POSES[4]):
-        _check(cv, orc, ow, ew, setup_for(cv, terrain_world, spec, W, H), W, H, spec[0], variants=(0,), groups=(8, 16))
+        _check(cv, orc, ow, ew, setup_for(cv, terrain_world, spec, W, H), W, H, spec[0], groups=(8, 16))
 
 
 def test_emulated_tall_columns_and_near_plane(cv, orc):

@@ -28,9 +28,9 @@ void body_g(void* p) {
     if (a->variant == 0) {
         if (a->counters) phase1_kernel<G, true, false, false>(*a->world, *a->frame);
         else phase1_kernel<G, false, false, false>(*a->world, *a->frame);
-    } else if (G == 32) {
-        if (a->counters) phase1_kernel<32, true, false, true>(*a->world, *a->frame);
-        else phase1_kernel<32, false, false, true>(*a->world, *a->frame);
+    } else {
+        if (a->counters) phase1_kernel<G, true, false, true>(*a->world, *a->frame);
+        else phase1_kernel<G, false, false, true>(*a->world, *a->frame);
     }
 }
 
@@ -75,7 +75,6 @@ int emu_phase1(const emu_world* w, const cvx_frame_setup* setup, int W, int H, u
     f.ray_begin = ray_begin; f.ray_end = ray_end;
     const int n = ray_end - ray_begin;
     if (n <= 0) return 0;
-    if (variant == 1) group = 32;
     if (group != 8 && group != 16 && group != 32) group = 32;
     const int groupsPerCta = CVXD_THREADS_PER_CTA / group;
     const int blocks = (n + groupsPerCta - 1) / groupsPerCta;
