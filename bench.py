@@ -9,12 +9,16 @@ at 3840x2160 — BASELINE config 1 at the north_star's headline resolution; 1080
 A step = one pass over the 60 poses (60 frames). Synthetic data only in the sense of the fixed camera path; the world is
 the reference's shipped dataset.
 
-value    frames/s with everything resident in HBM: per frame one Phase-1 and one Phase-2 launch through cvx_draw.
+value    frames/s with everything resident in HBM: per frame one Phase-1 and one Phase-2 launch; a step is one
+         cvx_draw_batch over the 60 poses (device only), which keeps up to `frames_in_flight` views in flight, each on its own
+         stream with its own raybuffers and framebuffer (the reference double-buffers its raybuffers for the same overlap).
 e2e      frames/s through the public C ABI with HOST buffers: per frame the host computes the segment/VP setup
          (cvx_host_frame_setup), passes it by value (kernel parameters are the only host->device bytes) and receives the
          finished frame in pinned host memory (cvx_draw_batch, copy overlapped with the next frame's kernels).
-roofline Phase-1 kernel (dominant): algorithmic bytes of SURVEY.md §8(d) per launch / mean launch duration (CUDA events
-         around every launch inside the timed region) against the measured HBM copy bandwidth of MEASURED_PEAKS.json.
+roofline Phase-1 kernel (dominant): algorithmic bytes of SURVEY.md §8(d) per launch / launch duration against the measured
+         HBM copy bandwidth of MEASURED_PEAKS.json. Launches of different views overlap, so the duration used is the timed
+         region's wall time per frame times Phase 1's share of the summed kernel time (CUDA events around every launch inside
+         the timed region); "exclusive" repeats the measurement with one view in flight (each launch alone on the GPU).
 cpu_baseline / --impl reference: the CPU restatement of the reference's path (oracle/, "port": the reference is C# on
          Unity/Burst and cannot be built here) on all host threads.
 N > 1    views are sharded (each rank renders the whole path for its own share of a global batch of N x 60 views), the
@@ -51,6 +55,7 @@ def parse_args():
     ap.add_argument("--res", default="3840x2160")
     ap.add_argument("--maxdim", type=int, default=1024)
     ap.add_argument("--group", type=int, default=0, help="Phase-1 lanes per ray (0 = library default)")
+    ap.add_argument("--inflight", type=int, default=4, help="views in flight per cvx_draw_batch (1..8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-1080p", action="store_true")
     return ap.parse_args()
@@ -165,9 +170,8 @@ def run_reference(a, rank, world_size):
 def time_path(torch, dist, rm, setups, steps, warmup, device, flush, world_size, profile=True):
     """W warm-up steps, then exactly `steps` steps between barrier+synchronize pairs; CUDA events on the launching stream."""
     def one_step():
-        flush.zero_()  # L2 flush between steps: 256 MiB written on the same stream
-        for s in setups:
-            rm.draw_setup(s)
+        flush.zero_()            # L2 flush between steps: 256 MiB written on the same stream
+        rm.draw_batch(setups)    # device only: enqueues all views, joined back into this stream
 
     for _ in range(warmup):
         one_step()
@@ -244,6 +248,7 @@ def run_b200(a, rank, local_rank, world_size):
     rm.set_stream(stream.cuda_stream)
     rm.upload_world(world)
     rm.set_group_size(a.group)
+    rm.set_frames_in_flight(a.inflight)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=f"cuda:{device}")
     poses = cv.benchmark_path(world.dims, FRAMES_PER_STEP, far_clip=2.0 * world.max_dimension)
 
@@ -269,14 +274,18 @@ def run_b200(a, rank, local_rank, world_size):
         ms, p1, p2, n, launches, span = time_path(torch, dist, rm, setups, steps, a.warmup, device, flush, world_size)
         if sampler:
             clocks = sampler.stop(*span)
+        # the same launches one view at a time: exclusive kernel durations (outside the timed region, reported beside it)
+        rm.set_frames_in_flight(1)
+        _, x1, x2, xn, _, _ = time_path(torch, dist, rm, setups, 1, 1, device, flush, world_size)
+        rm.set_frames_in_flight(a.inflight)
         pinned = cv.alloc_pinned((len(poses), h, w))
         e2e_s = time_e2e(torch, dist, cv, rm, poses, steps, a.warmup, device, world_size, pinned)
         N.lib.cvx_free_pinned(pinned.ctypes.data)
-        t = torch.tensor([ms, e2e_s * 1000.0, p1, p2], dtype=torch.float64, device=f"cuda:{device}")
+        t = torch.tensor([ms, e2e_s * 1000.0, p1, p2, x1, x2], dtype=torch.float64, device=f"cuda:{device}")
         if world_size > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
-        ms, e2e_ms, p1, p2 = [float(x) for x in t.cpu()]
-        results[(w, h)] = dict(ms=ms, e2e_ms=e2e_ms, p1=p1, p2=p2, n=n, launches=launches, steps=steps, per=per)
+        ms, e2e_ms, p1, p2, x1, x2 = [float(x) for x in t.cpu()]
+        results[(w, h)] = dict(ms=ms, e2e_ms=e2e_ms, p1=p1, p2=p2, n=n, launches=launches, steps=steps, per=per, x1=x1, x2=x2, xn=xn)
 
     main = results[(W, H)]
     steps = main["steps"]
@@ -286,8 +295,12 @@ def run_b200(a, rank, local_rank, world_size):
     per = main["per"]
     runs_per_frame = sum(c["runs_visited"] for c in per) / len(per)
     p1_bytes = sum(phase1_bytes(c) for c in per) / len(per)             # mean algorithmic bytes per Phase-1 launch
-    p1_ms = main["p1"] / max(1, main["n"])                              # mean Phase-1 launch duration (CUDA events, timed region)
-    p2_ms = main["p2"] / max(1, main["n"])
+    p1_ev = main["p1"] / max(1, main["n"])                              # mean Phase-1 launch duration by CUDA events (launches overlap)
+    p2_ev = main["p2"] / max(1, main["n"])
+    frame_ms = main["ms"] / (steps * FRAMES_PER_STEP)                    # timed-region wall time per frame on this rank
+    share = p1_ev / (p1_ev + p2_ev) if p1_ev + p2_ev > 0 else 1.0
+    p1_ms, p2_ms = frame_ms * share, frame_ms * (1.0 - share)           # effective duration per launch under overlap
+    x1_ms, x2_ms = main["x1"] / max(1, main["xn"]), main["x2"] / max(1, main["xn"])   # one view in flight: each launch alone
     peak, peak_src = measured_hbm_peak()
     achieved = p1_bytes / (p1_ms * 1e-3) / 1e9 if p1_ms > 0 else 0.0
     frame_bytes = sum(cv.algorithmic_bytes(c, W, H) for c in per) / len(per)
@@ -305,13 +318,19 @@ def run_b200(a, rank, local_rank, world_size):
             "workload": workload_name(a.maxdim, W, H), "resolution": [W, H], "frames_per_step": FRAMES_PER_STEP * world_size,
             "parallelism": "1 GPU" if world_size == 1 else f"views sharded over {world_size} GPUs, world broadcast once and replicated, no data-path collective",
             "l2": "flushed between steps (256 MiB device write inside the timed region); frames of one step run back to back",
-            "phase1_lanes_per_ray": a.group or 32,
+            "phase1_lanes_per_ray": a.group or 32, "frames_in_flight": a.inflight,
         },
         "runs_per_s": runs_per_frame * fps,
-        "ms_per_frame": {"total": main["ms"] / (steps * FRAMES_PER_STEP), "phase1_kernel": p1_ms, "phase2_kernel": p2_ms},
+        "ms_per_frame": {"total": frame_ms, "phase1_kernel": p1_ms, "phase2_kernel": p2_ms,
+                         "basis": "wall time of the timed region per frame, split by the kernels' share of summed CUDA-event durations "
+                                  f"(up to {a.inflight} views in flight, launches overlap)",
+                         "event_mean_overlapped": {"phase1_kernel": p1_ev, "phase2_kernel": p2_ev},
+                         "exclusive_one_view_in_flight": {"phase1_kernel": x1_ms, "phase2_kernel": x2_ms}},
         "roofline": {
             "bound": "hbm", "kernel": "phase1_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "peak_source": peak_src, "algorithmic_bytes_per_launch": p1_bytes, "traffic": ncu_traffic(W),
+            "exclusive": {"launch_ms": x1_ms, "achieved": p1_bytes / (x1_ms * 1e-3) / 1e9 if x1_ms > 0 else 0.0,
+                          "note": "same launches with one view in flight (each alone on the GPU), measured after the timed region"},
             "whole_frame": {"algorithmic_bytes": frame_bytes, "achieved": frame_bytes * fps / world_size / 1e9,
                             "frac": frame_bytes * fps / world_size / 1e9 / peak},
         },
@@ -325,7 +344,7 @@ def run_b200(a, rank, local_rank, world_size):
         r = results[(1920, 1080)]
         fr = FRAMES_PER_STEP * r["steps"] * world_size
         line["at_1080p"] = {"value": fr / (r["ms"] / 1000.0), "unit": "frames/s", "e2e": fr / (r["e2e_ms"] / 1000.0),
-                            "phase1_kernel_ms": r["p1"] / max(1, r["n"]), "phase2_kernel_ms": r["p2"] / max(1, r["n"]),
+                            "phase1_kernel_ms_exclusive": r["x1"] / max(1, r["xn"]), "phase2_kernel_ms_exclusive": r["x2"] / max(1, r["xn"]),
                             "runs_per_s": sum(c["runs_visited"] for c in r["per"]) / len(r["per"]) * fr / (r["ms"] / 1000.0)}
 
     if world_size == 1 and not a.no_cpu_baseline:

@@ -23,11 +23,22 @@ static_assert(sizeof(cvx_ray_state) == sizeof(cvxd_ray_state), "ray state layout
 static_assert(sizeof(cvx_counters) == sizeof(cvxd_counters), "counter layout");
 static_assert(CVX_LOD_LEVELS == CVXD_LODS, "lod levels");
 
+#define CVX_MAX_SLOTS 8
+#define CVX_DEFAULT_SLOTS 4
+
+struct cvx_slot {
+    cudaStream_t stream = nullptr;
+    uint32_t* td = nullptr;
+    uint32_t* lr = nullptr;
+    uint32_t* frame = nullptr;
+    cudaEvent_t done = nullptr;
+};
+
 struct cvx_ctx {
     int device = 0;
     int flags = 0;
     cudaStream_t stream = nullptr;      // compute
-    cudaStream_t copyStream = nullptr;  // device->host frame copies of cvx_draw_batch
+    cudaStream_t copyStream = nullptr;  // (kept for cvx_sync symmetry; frame copies ride on the slot streams)
     bool ownStream = true;
     cvxd_world world;
     void* lodHeaders[CVX_LOD_LEVELS];
@@ -37,7 +48,14 @@ struct cvx_ctx {
     int width = 0, height = 0;
     uint32_t* td = nullptr;
     uint32_t* lr = nullptr;
-    uint32_t* frames[2] = {nullptr, nullptr}; // internal framebuffers (double buffered for batches)
+    uint32_t* frames[2] = {nullptr, nullptr}; // internal framebuffer (index 0; index 1 unused)
+    // cvx_draw_batch keeps several views in flight: view i renders on slot i % slotCount, each slot a stream with its own
+    // raybuffers and framebuffer. Slot 0 is the context's stream and buffers; the others are allocated on first use.
+    cvx_slot extra[CVX_MAX_SLOTS - 1];
+    int slotCount = CVX_DEFAULT_SLOTS;  // CVX_OPT_FRAMES_IN_FLIGHT
+    int extraReady = 0;                 // extra slots holding buffers for the current resolution
+    int lastSlot = 0;                   // slot of the most recent view (what the read functions return)
+    cudaEvent_t evBatchStart = nullptr;
     uint32_t* externalFrame = nullptr;
     int frameIndex = 0;
     cvxd_counters* counters = nullptr;
@@ -110,9 +128,52 @@ int check_ready(cvx_ctx* ctx, const void* setup) {
     return CVX_OK;
 }
 
-uint32_t* current_target(cvx_ctx* ctx) { return ctx->externalFrame ? ctx->externalFrame : ctx->frames[ctx->frameIndex]; }
+cudaStream_t slot_stream(cvx_ctx* ctx, int s) { return s == 0 ? ctx->stream : ctx->extra[s - 1].stream; }
+uint32_t* slot_td(cvx_ctx* ctx, int s) { return s == 0 ? ctx->td : ctx->extra[s - 1].td; }
+uint32_t* slot_lr(cvx_ctx* ctx, int s) { return s == 0 ? ctx->lr : ctx->extra[s - 1].lr; }
+uint32_t* slot_frame(cvx_ctx* ctx, int s) { return s == 0 ? ctx->frames[0] : ctx->extra[s - 1].frame; }
+
+uint32_t* current_target(cvx_ctx* ctx) { return ctx->externalFrame ? ctx->externalFrame : slot_frame(ctx, ctx->lastSlot); }
+
+void free_extra_slots(cvx_ctx* ctx) {
+    for (int i = 0; i < CVX_MAX_SLOTS - 1; i++) {
+        cvx_slot& sl = ctx->extra[i];
+        if (sl.stream) cudaStreamSynchronize(sl.stream);
+        cudaFree(sl.td); cudaFree(sl.lr); cudaFree(sl.frame);
+        sl.td = sl.lr = sl.frame = nullptr;
+    }
+    ctx->extraReady = 0;
+    ctx->lastSlot = 0;
+}
+
+// slots 1 .. want-1 get a stream, an event and zero-initialised buffers of the current resolution
+int ensure_slots(cvx_ctx* ctx, int want) {
+    if (want > ctx->slotCount) want = ctx->slotCount;
+    const size_t W = (size_t)ctx->width, H = (size_t)ctx->height;
+    const size_t tdBytes = H * (W + 2 * H) * 4, lrBytes = W * (2 * W + H) * 4, fbBytes = W * H * 4;
+    while (ctx->extraReady < want - 1) {
+        cvx_slot& sl = ctx->extra[ctx->extraReady];
+        cudaError_t e = cudaSuccess;
+        if (!sl.stream) e = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess && !sl.done) e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaMalloc(&sl.td, tdBytes);
+        if (e == cudaSuccess) e = cudaMalloc(&sl.lr, lrBytes);
+        if (e == cudaSuccess) e = cudaMalloc(&sl.frame, fbBytes);
+        if (e == cudaSuccess) e = cudaMemsetAsync(sl.td, 0, tdBytes, sl.stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(sl.lr, 0, lrBytes, sl.stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(sl.frame, 0, fbBytes, sl.stream);
+        if (e != cudaSuccess) {
+            cudaFree(sl.td); cudaFree(sl.lr); cudaFree(sl.frame);
+            sl.td = sl.lr = sl.frame = nullptr;
+            return fail(ctx, e == cudaErrorMemoryAllocation ? CVX_ERR_OUT_OF_MEMORY : CVX_ERR_CUDA, "frame slot allocation failed: %s", cudaGetErrorString(e));
+        }
+        ctx->extraReady++;
+    }
+    return CVX_OK;
+}
 
 void free_resolution(cvx_ctx* ctx) {
+    free_extra_slots(ctx);
     cudaFree(ctx->td); cudaFree(ctx->lr); cudaFree(ctx->frames[0]); cudaFree(ctx->frames[1]);
     ctx->td = ctx->lr = ctx->frames[0] = ctx->frames[1] = nullptr;
     ctx->width = ctx->height = 0;
@@ -156,6 +217,7 @@ int cvx_create(const cvx_config* config, cvx_ctx** out_ctx) {
     CREATE_CU(cudaEventCreate(&ctx->evStart));
     CREATE_CU(cudaEventCreate(&ctx->evMid));
     CREATE_CU(cudaEventCreate(&ctx->evEnd));
+    CREATE_CU(cudaEventCreateWithFlags(&ctx->evBatchStart, cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) {
         CREATE_CU(cudaEventCreateWithFlags(&ctx->evFrameDone[i], cudaEventDisableTiming));
         CREATE_CU(cudaEventCreateWithFlags(&ctx->evCopyDone[i], cudaEventDisableTiming));
@@ -179,6 +241,11 @@ int cvx_destroy(cvx_ctx* ctx) {
     if (ctx->evStart) cudaEventDestroy(ctx->evStart);
     if (ctx->evMid) cudaEventDestroy(ctx->evMid);
     if (ctx->evEnd) cudaEventDestroy(ctx->evEnd);
+    if (ctx->evBatchStart) cudaEventDestroy(ctx->evBatchStart);
+    for (int i = 0; i < CVX_MAX_SLOTS - 1; i++) {
+        if (ctx->extra[i].done) cudaEventDestroy(ctx->extra[i].done);
+        if (ctx->extra[i].stream) cudaStreamDestroy(ctx->extra[i].stream);
+    }
     for (int i = 0; i < 2; i++) {
         if (ctx->evFrameDone[i]) cudaEventDestroy(ctx->evFrameDone[i]);
         if (ctx->evCopyDone[i]) cudaEventDestroy(ctx->evCopyDone[i]);
@@ -272,11 +339,9 @@ int cvx_set_resolution(cvx_ctx* ctx, int32_t width, int32_t height) {
     cudaError_t e = cudaMalloc(&ctx->td, tdBytes);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->lr, lrBytes);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->frames[0], fbBytes);
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->frames[1], fbBytes);
     if (e == cudaSuccess) e = cudaMemsetAsync(ctx->td, 0, tdBytes, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(ctx->lr, 0, lrBytes, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(ctx->frames[0], 0, fbBytes, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->frames[1], 0, fbBytes, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         free_resolution(ctx);
@@ -295,6 +360,7 @@ int cvx_draw_rays(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t ray_begin,
     if (ray_end < 0 || ray_end > f.total_rays) ray_end = f.total_rays;
     if (ray_begin < 0) ray_begin = 0;
     f.ray_begin = ray_begin; f.ray_end = ray_end;
+    ctx->lastSlot = 0;
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaEventRecord(ctx->evStart, ctx->stream));
     CU(ctx, cvxd_launch_phase1(ctx->world, f, ctx->groupSize, ctx->stream));
@@ -337,25 +403,29 @@ int cvx_blit_owned(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t ray_begin
     return CVX_OK;
 }
 
-static int draw_into(cvx_ctx* ctx, const cvx_frame_setup* setup, uint32_t* target, bool timed) {
+static int draw_into(cvx_ctx* ctx, const cvx_frame_setup* setup, int slot, uint32_t* target, bool timed) {
     cvxd_frame f;
     make_frame(ctx, setup, f);
+    f.td = slot_td(ctx, slot); f.lr = slot_lr(ctx, slot);
     int r = validate_setup(ctx, setup, f.total_rays);
     if (r) return r;
     cvxd_blit b;
     make_blit(ctx, f, target, b);
+    b.td = f.td; b.lr = f.lr;
+    cudaStream_t stream = slot_stream(ctx, slot);
     const bool prof = ctx->profCount < ctx->profCapacity;
     cudaEvent_t* pe = prof ? &ctx->profEvents[3 * (size_t)ctx->profCount] : nullptr;
-    if (timed) CU(ctx, cudaEventRecord(ctx->evStart, ctx->stream));
-    if (prof) CU(ctx, cudaEventRecord(pe[0], ctx->stream));
-    CU(ctx, cvxd_launch_phase1(ctx->world, f, ctx->groupSize, ctx->stream));
+    if (timed) CU(ctx, cudaEventRecord(ctx->evStart, stream));
+    if (prof) CU(ctx, cudaEventRecord(pe[0], stream));
+    CU(ctx, cvxd_launch_phase1(ctx->world, f, ctx->groupSize, stream));
     if (f.total_rays > 0) ctx->launches++;
-    if (timed) CU(ctx, cudaEventRecord(ctx->evMid, ctx->stream));
-    if (prof) CU(ctx, cudaEventRecord(pe[1], ctx->stream));
-    CU(ctx, cvxd_launch_phase2(b, ctx->stream));
+    if (timed) CU(ctx, cudaEventRecord(ctx->evMid, stream));
+    if (prof) CU(ctx, cudaEventRecord(pe[1], stream));
+    CU(ctx, cvxd_launch_phase2(b, stream));
     ctx->launches++;
-    if (timed) { CU(ctx, cudaEventRecord(ctx->evEnd, ctx->stream)); ctx->timed = true; }
-    if (prof) { CU(ctx, cudaEventRecord(pe[2], ctx->stream)); ctx->profCount++; }
+    if (timed) { CU(ctx, cudaEventRecord(ctx->evEnd, stream)); ctx->timed = true; }
+    if (prof) { CU(ctx, cudaEventRecord(pe[2], stream)); ctx->profCount++; }
+    ctx->lastSlot = slot;
     return CVX_OK;
 }
 
@@ -363,32 +433,37 @@ int cvx_draw(cvx_ctx* ctx, const cvx_frame_setup* setup) {
     int r = check_ready(ctx, setup);
     if (r) return r;
     CU(ctx, cudaSetDevice(ctx->device));
-    return draw_into(ctx, setup, current_target(ctx), true);
+    ctx->lastSlot = 0;
+    return draw_into(ctx, setup, 0, current_target(ctx), true);
 }
 
 int cvx_draw_batch(cvx_ctx* ctx, const cvx_frame_setup* setups, int32_t n_views, void* dst_frames) {
     int r = check_ready(ctx, setups);
     if (r) return r;
     if (n_views < 0) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "n_views < 0");
+    if (n_views == 0) return CVX_OK;
     CU(ctx, cudaSetDevice(ctx->device));
     const size_t fbBytes = (size_t)ctx->width * ctx->height * 4;
-    if (!dst_frames) { // device only: frames overwrite each other in the current target
-        for (int i = 0; i < n_views; i++) if ((r = draw_into(ctx, setups + i, current_target(ctx), false))) return r;
-        return CVX_OK;
-    }
-    // pipelined: view i renders into internal buffer i&1 on the compute stream while view i-1 is copied to the host
-    // on the copy stream. The copy is asynchronous only if dst_frames is page-locked (cvx_alloc_pinned / cudaHostRegister).
+    // View i renders on slot i % K: Phase 1, Phase 2 and (with dst_frames) the device->host copy of its frame are stream-ordered
+    // inside the slot, and the K slots overlap each other — the long tail of one view's few heavy rays runs beside the bulk of
+    // the next views, and frame copies run beside kernels. A caller-owned external frame forces one slot (one target buffer).
+    const int K = ctx->externalFrame ? 1 : (ctx->slotCount < n_views ? ctx->slotCount : n_views);
+    if ((r = ensure_slots(ctx, K))) return r;
+    CU(ctx, cudaEventRecord(ctx->evBatchStart, ctx->stream)); // the slots start after everything queued on the context's stream
+    for (int s = 1; s < K; s++) CU(ctx, cudaStreamWaitEvent(slot_stream(ctx, s), ctx->evBatchStart, 0));
     for (int i = 0; i < n_views; i++) {
-        const int slot = i & 1;
-        if (i >= 2) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evCopyDone[slot], 0)); // buffer free again
-        if ((r = draw_into(ctx, setups + i, ctx->frames[slot], false))) return r;
-        CU(ctx, cudaEventRecord(ctx->evFrameDone[slot], ctx->stream));
-        CU(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evFrameDone[slot], 0));
-        CU(ctx, cudaMemcpyAsync((uint8_t*)dst_frames + (size_t)i * fbBytes, ctx->frames[slot], fbBytes, cudaMemcpyDeviceToHost, ctx->copyStream));
-        CU(ctx, cudaEventRecord(ctx->evCopyDone[slot], ctx->copyStream));
+        const int slot = i % K;
+        uint32_t* target = ctx->externalFrame ? ctx->externalFrame : slot_frame(ctx, slot);
+        if ((r = draw_into(ctx, setups + i, slot, target, false))) return r;
+        // the copy is asynchronous only if dst_frames is page-locked (cvx_alloc_pinned / cudaHostRegister)
+        if (dst_frames) CU(ctx, cudaMemcpyAsync((uint8_t*)dst_frames + (size_t)i * fbBytes, target, fbBytes, cudaMemcpyDeviceToHost, slot_stream(ctx, slot)));
     }
-    CU(ctx, cudaStreamSynchronize(ctx->copyStream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    // join: whatever the caller queues next on the context's stream (events, reads, the next batch) comes after all views
+    for (int s = 1; s < K; s++) {
+        CU(ctx, cudaEventRecord(ctx->extra[s - 1].done, slot_stream(ctx, s)));
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->extra[s - 1].done, 0));
+    }
+    if (dst_frames) CU(ctx, cudaStreamSynchronize(ctx->stream)); // frames are on the host when the call returns
     return CVX_OK;
 }
 
@@ -418,7 +493,7 @@ int cvx_read_raybuffer(cvx_ctx* ctx, int32_t which, void* dst_argb, int64_t byte
     const int64_t full = which == 0 ? H * (W + 2 * H) * 4 : W * (2 * W + H) * 4;
     const int64_t n = bytes < full ? bytes : full;
     CU(ctx, cudaSetDevice(ctx->device));
-    CU(ctx, cudaMemcpyAsync(dst_argb, which == 0 ? ctx->td : ctx->lr, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(dst_argb, which == 0 ? slot_td(ctx, ctx->lastSlot) : slot_lr(ctx, ctx->lastSlot), (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return CVX_OK;
 }
@@ -455,7 +530,7 @@ int cvx_device_raybuffer(cvx_ctx* ctx, int32_t which, void** out_device_ptr, int
     if (!ctx || !out_device_ptr || which < 0 || which > 1) return CVX_ERR_INVALID_ARGUMENT;
     if (ctx->width <= 0) return fail(ctx, CVX_ERR_NO_RESOLUTION, "no resolution set");
     const int64_t W = ctx->width, H = ctx->height;
-    *out_device_ptr = which == 0 ? ctx->td : ctx->lr;
+    *out_device_ptr = which == 0 ? slot_td(ctx, ctx->lastSlot) : slot_lr(ctx, ctx->lastSlot);
     if (out_bytes) *out_bytes = which == 0 ? H * (W + 2 * H) * 4 : W * (2 * W + H) * 4;
     return CVX_OK;
 }
@@ -495,6 +570,10 @@ int cvx_set_option(cvx_ctx* ctx, int32_t option, int32_t value) {
         return CVX_OK;
     case CVX_OPT_COUNTERS:
         ctx->flags = value ? (ctx->flags | CVX_FLAG_COUNTERS) : (ctx->flags & ~CVX_FLAG_COUNTERS);
+        return CVX_OK;
+    case CVX_OPT_FRAMES_IN_FLIGHT:
+        if (value < 1 || value > CVX_MAX_SLOTS) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "frames in flight %d: expected 1..%d", value, CVX_MAX_SLOTS);
+        ctx->slotCount = value;
         return CVX_OK;
     case CVX_OPT_GENERAL_PATH:
         ctx->generalPath = value ? 1 : 0;

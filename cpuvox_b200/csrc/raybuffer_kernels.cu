@@ -31,6 +31,12 @@
 #include "device_types.h"
 
 #define FULL_MASK 0xffffffffu
+#if defined(CVX_EMU) && defined(CVX_EMU_STATS) /* emulator-only event counts per ray (tools/simt_emu), lane 0 of the group counts */
+#define EMU_STAT(i) do { if (gl == 0) emu_stats[(int64_t)flat * 16 + (i)]++; } while (0)
+extern unsigned long long* emu_stats;
+#else
+#define EMU_STAT(i) do { } while (0)
+#endif
 #define SKYBOX_ARGB 0x191919FFu /* ColorARGB32(25,25,25): bytes a=255,r,g,b (DrawSegmentRayJob.cs:702) */
 
 namespace {
@@ -448,6 +454,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
         bool reachedEnd = false; // far clip or world exit
         while (!terminated && !reachedEnd) {
             STAMP(1);
+            EMU_STAT(0); // batches
             // ---- look ahead: the next G cells of the DDA at once, lane k of the group gets cell k -------------------------
             // Step() (SegmentDDAData.cs:135-150) crosses the x boundary when tMax.x < tMax.y, else the z boundary, and then adds
             // tDelta to that tMax: the crossing times are the merge of the two sequences X[a] = tMax.x + a additions of tDelta.x and
@@ -562,6 +569,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
 
             while (remaining) {
                 STAMP(2);
+                EMU_STAT(1); // select iterations
                 // ---- next column that is not culled by the narrowed frustum (:261-281), found for all columns at once ----
                 int c;
                 float worldBoundsMin = 0.0f, worldBoundsMax = worldMaxY;
@@ -604,6 +612,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
 
                 if (distLast > 2.0f && frustumDirMaxWorld == EPS) { // re-narrow the frustum :295-422
                     STAMP(3);
+                    EMU_STAT(2); // renarrows
                     // The four clip parameters (last/next line x min/max end) and their projections are independent:
                     // lane L&3 of the group computes one of them (same operations as CameraData.cs:50-121), then they are shared.
                     const int L = gl & 3;
@@ -671,11 +680,13 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                 bool colStop = false;
                 do {
                     STAMP(4);
+                    EMU_STAT(3); // column passes
                     const int runsHere = tall ? (FAST ? (runCount - k0 < G - 1 ? runCount - k0 : G - 1) : (runCount - k0 < G ? runCount - k0 : G)) : runCount;
                     if (tall || !((roundCols >> c) & 1u)) {
                         // ---- form a round: this column (pass) plus, if it is not a tall one, the following columns that are likely
                         // to be entered, as long as their runs fit in the G lanes. One run per lane: fetch, world-Y bounds (segmented
                         // prefix sum), and the projected side/cap spans — the float-heavy part — once for all of them.
+                        EMU_STAT(4); // rounds formed
                         uint32_t follow = (CVXD_MULTI_COL && !tall) ? remaining : 0u;
                         if (follow && frustumDirMaxWorld != EPS) {
                             const float distTop = frustumDirMaxWorld > 0.0f ? myDn : myDl;
@@ -776,6 +787,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                                 if (r_capKind) r_capColor = __ldg(colElems + colRuns + 2 + (r_capKind == 1 ? r_ci : r_ci + r_len - 1)); // :553,560
                             }
                             if (GBALLOT(needExact)) {
+                                EMU_STAT(8); // rounds with a run straddling the near plane
                                 // ---- a run straddles the near plane: the reference's per-run clipping (rare; columns next to the camera)
                                 const F3 nF = F3{__shfl_down_sync(gmask, Fp.x, 1, G), __shfl_down_sync(gmask, Fp.y, 1, G), __shfl_down_sync(gmask, Fp.z, 1, G)};
                                 const F3 nN = F3{__shfl_down_sync(gmask, Np.x, 1, G), __shfl_down_sync(gmask, Np.y, 1, G), __shfl_down_sync(gmask, Np.z, 1, G)};
@@ -901,7 +913,10 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                         const int j = isCap ? jC : jS;
                         if (isCap) candC &= candC - 1u; else candS &= candS - 1u;
                         int bMin = GSHFL(isCap ? r_cMin : r_sMin, j), bMax = GSHFL(isCap ? r_cMax : r_sMax, j);
+                        EMU_STAT(5); // commit candidates examined
                         if (!span_would_write(rw, bMin, bMax)) continue; // written over / cut off since the round was formed
+                        EMU_STAT(6); // spans committed (each writes at least one pixel)
+                        if (isCap) EMU_STAT(7);
                         reduce_pixel_horizon(rw, bMin, bMax); // :507-517 / :583-593
                         if (isCap) {
                             const uint32_t color = FAST ? GSHFL(r_capColor, j) : cache[7 * G + j];

@@ -242,6 +242,8 @@ class RenderManager:
         self._ck(lib.cvx_blit_owned(self._ctx, C.byref(setup), ray_begin, ray_end, C.c_void_p(device_frame)))
 
     def draw_batch(self, setups: Sequence[FrameSetup], dst: Optional[np.ndarray] = None):
+        """cvx_draw_batch: with `dst` (pinned host array, one frame per view) returns when all frames are on the host; without,
+        only enqueues (the frames stay on the device; read_frame / read_raybuffers return the last view)."""
         arr = (FrameSetup * len(setups))(*setups)
         self._ck(lib.cvx_draw_batch(self._ctx, arr, len(setups), _ptr(dst) if dst is not None else None))
 
@@ -285,6 +287,10 @@ class RenderManager:
 
     def set_counters(self, on: bool):
         self.set_option(N.OPT_COUNTERS, int(on))
+
+    def set_frames_in_flight(self, k: int):
+        """Views of one draw_batch rendered concurrently (1..8, default 4), each on its own stream and buffer set."""
+        self.set_option(N.OPT_FRAMES_IN_FLIGHT, k)
 
     def set_general_path(self, on: bool):
         """True = always run the general Phase-1 kernel; False (default) = boundary-table kernel for regular worlds."""

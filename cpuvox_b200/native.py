@@ -73,6 +73,7 @@ FLAG_COUNTERS = 1
 OPT_GROUP_SIZE = 1
 OPT_COUNTERS = 2
 OPT_GENERAL_PATH = 3
+OPT_FRAMES_IN_FLIGHT = 4
 
 
 class Pose(C.Structure):

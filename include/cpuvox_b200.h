@@ -120,8 +120,10 @@ int cvx_blit_rows(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t row_begin,
  * device_frame (a W*H*4 device buffer, possibly a peer GPU's mapped framebuffer; NULL = own frame).
  * Ranks with disjoint ray ranges write disjoint pixels, so the gather is the store itself. */
 int cvx_blit_owned(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t ray_begin, int32_t ray_end, void* device_frame);
-/* Batched views over one world: n frames back to back, frame i
- * read back (if dst_frames != NULL) to dst_frames + i*W*H*4. */
+/* Batched views over one world: n frames, up to CVX_OPT_FRAMES_IN_FLIGHT of them in flight at
+ * once; frame i is read back (if dst_frames != NULL) to dst_frames + i*W*H*4 and the call returns when all frames are on the
+ * host. With dst_frames == NULL the call only enqueues: the frames stay on the device (the read functions and device
+ * pointers refer to the LAST view), ordered before anything queued later on the context's stream. */
 int cvx_draw_batch(cvx_ctx* ctx, const cvx_frame_setup* setups, int32_t n_views, void* dst_frames);
 int cvx_sync(cvx_ctx* ctx);
 
@@ -153,10 +155,14 @@ int64_t cvx_launch_count(const cvx_ctx* ctx);
  *   CVX_OPT_GROUP_SIZE  lanes cooperating on one ray in Phase 1: 0 = choose per frame from the ray count, or 8, 16, 32.
  *   CVX_OPT_COUNTERS    1 = accumulate cvx_counters (same as CVX_FLAG_COUNTERS at creation), 0 = off.
  *   CVX_OPT_GENERAL_PATH 1 = always run the general Phase-1 kernel (reads the reference element area run by run); 0 (default) =
- *                       use the boundary-table kernel whenever the uploaded world is regular (see cvx_world_is_regular). */
+ *                       use the boundary-table kernel whenever the uploaded world is regular (see cvx_world_is_regular).
+ *   CVX_OPT_FRAMES_IN_FLIGHT 1..8 (default 4): views of one cvx_draw_batch rendered concurrently, each on its own stream with its
+ *                       own raybuffers and framebuffer (the reference double-buffers its raybuffers for the same reason,
+ *                       RenderManager.cs:14,53-56). Extra buffer sets are allocated on the first batch that needs them. */
 #define CVX_OPT_GROUP_SIZE 1
 #define CVX_OPT_COUNTERS 2
 #define CVX_OPT_GENERAL_PATH 3
+#define CVX_OPT_FRAMES_IN_FLIGHT 4
 int cvx_set_option(cvx_ctx* ctx, int32_t option, int32_t value);
 /* 1 when every uploaded LOD consists of full-height columns of valid runs (what WorldBuilder.ToFinalColumn emits,
  * WordBuilder.cs:232-256): Phase 1 then runs its boundary-table kernel. 0 = the general kernel is used. < 0 = error. */

@@ -177,6 +177,19 @@ def test_draw_batch_equals_individual_draws(cv, rm, mill_world):
     rm.draw_batch(setups, dst)
     for i, f in enumerate(singles):
         assert np.array_equal(dst[i], f), i
+    # every number of views in flight gives the same frames (views render concurrently on separate streams / buffer sets), and
+    # the device-only form leaves the LAST view's frame and raybuffers readable
+    for k in (1, 2, 3, 8):
+        rm.set_frames_in_flight(k)
+        dst[:] = 0
+        rm.draw_batch(setups, dst)
+        for i, f in enumerate(singles):
+            assert np.array_equal(dst[i], f), (k, i)
+        rm.draw_batch(setups)
+        assert np.array_equal(rm.read_frame(), singles[-1]), k
+    rm.set_frames_in_flight(4)
+    with pytest.raises(cv.CvxError):
+        rm.set_frames_in_flight(9)
 
 
 def test_ray_setup_state_matches_oracle(cv, orc, rm, mill_world):

@@ -8,6 +8,9 @@
 #include <thread>
 #include <vector>
 
+#ifdef CVX_EMU_STATS
+unsigned long long* emu_stats = nullptr;
+#endif
 #include "../../cpuvox_b200/csrc/raybuffer_kernels.cu"
 #include "../../cpuvox_b200/csrc/host_frame.h"
 #include "../../cpuvox_b200/csrc/world_transcode.h"
@@ -61,6 +64,9 @@ emu_world* emu_world_create(int lods, const int32_t dims[3], const void* const* 
     return w;
 }
 
+#ifdef CVX_EMU_STATS
+void emu_set_stats(unsigned long long* p) { emu_stats = p; } // 16 counters per flat ray
+#endif
 void emu_world_destroy(emu_world* w) { delete w; }
 int emu_world_regular(const emu_world* w) { return w->w.regular; }
 
