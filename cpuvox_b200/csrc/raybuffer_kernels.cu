@@ -629,7 +629,8 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                     if (crossHi || crossLo) {
                         const float fi = 1.0f / (crossHi ? rw.fb_max : rw.fb_min);
                         const float c0 = cross2(1.0f, fi, pMax.x, pMax.z), c1 = cross2(1.0f, fi, pMin.x, pMin.z);
-                        const float q = isMax ? c1 / (c1 - c0) : c0 / (c0 - c1);
+                        const float num = isMax ? c1 : c0, den = isMax ? c1 - c0 : c0 - c1; // one division: c1/(c1-c0) or c0/(c0-c1)
+                        const float q = num / den;
                         myLerp = isMax ? q : 1.0f - q;
                     }
                     const F3 pc = lerp3(pMin, pMax, myLerp);

@@ -13,7 +13,7 @@ import os
 LOD_LEVELS = 6  # UnityManager.LOD_LEVELS, Assets/Code/UnityManager.cs:42
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcpuvox_b200.so")
+LIB_PATH = os.environ.get("CPUVOX_B200_LIB") or os.path.join(_HERE, "libcpuvox_b200.so")  # the override is for kernel-variant A/B runs (tools/)
 
 
 class CvxError(RuntimeError):
