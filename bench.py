@@ -17,8 +17,8 @@ e2e      frames/s through the public C ABI with HOST buffers: per frame the host
          finished frame in pinned host memory (cvx_draw_batch, copy overlapped with the next frame's kernels).
 roofline Phase-1 kernel (dominant): algorithmic bytes of SURVEY.md §8(d) per launch / launch duration against the measured
          HBM copy bandwidth of MEASURED_PEAKS.json. Launches of different views overlap, so the duration used is the timed
-         region's wall time per frame times Phase 1's share of the summed kernel time (CUDA events around every launch inside
-         the timed region); "exclusive" repeats the measurement with one view in flight (each launch alone on the GPU).
+         region's wall time per frame times Phase 1's share of the kernel time; the share comes from the "exclusive" pass, which
+         repeats the launches with one view in flight (each launch alone on the GPU, CUDA events around every launch).
 cpu_baseline / --impl reference: the CPU restatement of the reference's path (oracle/, "port": the reference is C# on
          Unity/Burst and cannot be built here) on all host threads.
 N > 1    views are sharded (each rank renders the whole path for its own share of a global batch of N x 60 views), the
@@ -298,9 +298,11 @@ def run_b200(a, rank, local_rank, world_size):
     p1_ev = main["p1"] / max(1, main["n"])                              # mean Phase-1 launch duration by CUDA events (launches overlap)
     p2_ev = main["p2"] / max(1, main["n"])
     frame_ms = main["ms"] / (steps * FRAMES_PER_STEP)                    # timed-region wall time per frame on this rank
-    share = p1_ev / (p1_ev + p2_ev) if p1_ev + p2_ev > 0 else 1.0
-    p1_ms, p2_ms = frame_ms * share, frame_ms * (1.0 - share)           # effective duration per launch under overlap
     x1_ms, x2_ms = main["x1"] / max(1, main["xn"]), main["x2"] / max(1, main["xn"])   # one view in flight: each launch alone
+    # Phase 1's share of the step: from the EXCLUSIVE durations (the overlapped event durations of the short Phase-2 launches are
+    # inflated by the Phase-1 launches of the other views they share the GPU with, which would flatter Phase 1)
+    share = x1_ms / (x1_ms + x2_ms) if x1_ms + x2_ms > 0 else (p1_ev / (p1_ev + p2_ev) if p1_ev + p2_ev > 0 else 1.0)
+    p1_ms, p2_ms = frame_ms * share, frame_ms * (1.0 - share)           # effective duration per launch under overlap
     peak, peak_src = measured_hbm_peak()
     achieved = p1_bytes / (p1_ms * 1e-3) / 1e9 if p1_ms > 0 else 0.0
     frame_bytes = sum(cv.algorithmic_bytes(c, W, H) for c in per) / len(per)
@@ -322,7 +324,7 @@ def run_b200(a, rank, local_rank, world_size):
         },
         "runs_per_s": runs_per_frame * fps,
         "ms_per_frame": {"total": frame_ms, "phase1_kernel": p1_ms, "phase2_kernel": p2_ms,
-                         "basis": "wall time of the timed region per frame, split by the kernels' share of summed CUDA-event durations "
+                         "basis": "wall time of the timed region per frame, split by the kernels' share of the exclusive CUDA-event durations "
                                   f"(up to {a.inflight} views in flight, launches overlap)",
                          "event_mean_overlapped": {"phase1_kernel": p1_ev, "phase2_kernel": p2_ev},
                          "exclusive_one_view_in_flight": {"phase1_kernel": x1_ms, "phase2_kernel": x2_ms}},
