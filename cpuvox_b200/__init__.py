@@ -17,5 +17,6 @@ from .host import (  # noqa: F401
     benchmark_pose,
     frame_setup,
     setup_lods,
+    write_bmp,
 )
 from .parallel import ShardedRenderManager, broadcast_world, partition_rays, partition_views, ray_weights  # noqa: F401,E402

@@ -57,6 +57,7 @@ struct cvx_ctx {
     int lastSlot = 0;                   // slot of the most recent view (what the read functions return)
     cudaEvent_t evBatchStart = nullptr;
     uint32_t* externalFrame = nullptr;
+    uint32_t* presentStage = nullptr;   // cvx_present with a host destination: converted frame before the device->host copy
     int frameIndex = 0;
     cvxd_counters* counters = nullptr;
     cudaEvent_t evStart = nullptr, evMid = nullptr, evEnd = nullptr;
@@ -174,8 +175,8 @@ int ensure_slots(cvx_ctx* ctx, int want) {
 
 void free_resolution(cvx_ctx* ctx) {
     free_extra_slots(ctx);
-    cudaFree(ctx->td); cudaFree(ctx->lr); cudaFree(ctx->frames[0]); cudaFree(ctx->frames[1]);
-    ctx->td = ctx->lr = ctx->frames[0] = ctx->frames[1] = nullptr;
+    cudaFree(ctx->td); cudaFree(ctx->lr); cudaFree(ctx->frames[0]); cudaFree(ctx->frames[1]); cudaFree(ctx->presentStage);
+    ctx->td = ctx->lr = ctx->frames[0] = ctx->frames[1] = ctx->presentStage = nullptr;
     ctx->width = ctx->height = 0;
 }
 
@@ -472,6 +473,46 @@ int cvx_sync(cvx_ctx* ctx) {
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->copyStream));
+    return CVX_OK;
+}
+
+// Debug views: RayBufferBlit.shader COPY_MAIN1 / COPY_MAIN2 (:48-53), selected by UnityManager.ERenderMode.RayBufferTopDown /
+// RayBufferLeftRight (UnityManager.cs:129-134,471-483): the whole raybuffer of the last view stretched over the screen.
+int cvx_blit_raybuffer(cvx_ctx* ctx, int32_t which) {
+    if (!ctx || which < 0 || which > 1) return ctx ? fail(ctx, CVX_ERR_INVALID_ARGUMENT, "which must be 0 (top/down) or 1 (left/right)") : CVX_ERR_INVALID_ARGUMENT;
+    if (ctx->width <= 0) return fail(ctx, CVX_ERR_NO_RESOLUTION, "no resolution set");
+    const int W = ctx->width, H = ctx->height;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const uint32_t* buf = which == 0 ? slot_td(ctx, ctx->lastSlot) : slot_lr(ctx, ctx->lastSlot);
+    CU(ctx, cvxd_launch_raybuffer_view(buf, which == 0 ? W + 2 * H : 2 * W + H, which == 0 ? H : W, current_target(ctx), W, H, ctx->stream));
+    ctx->launches++;
+    return CVX_OK;
+}
+
+// Presentation: the step after the path. The reference ends in Unity's camera target; here the device frame is
+// converted to what a graphics API / video encoder takes (RGBA8 or BGRA8, top-down or bottom-up rows) on the device, and either
+// stays there (dst_is_device: a mapped graphics resource, an encoder input surface, a peer buffer) or is copied to the host.
+int cvx_present(cvx_ctx* ctx, int32_t format, int32_t top_down, void* dst, int32_t dst_is_device) {
+    if (!ctx || !dst) return ctx ? fail(ctx, CVX_ERR_INVALID_ARGUMENT, "dst is NULL") : CVX_ERR_INVALID_ARGUMENT;
+    if (format != CVX_PRESENT_RGBA8 && format != CVX_PRESENT_BGRA8) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "unknown present format %d", format);
+    if (ctx->width <= 0) return fail(ctx, CVX_ERR_NO_RESOLUTION, "no resolution set");
+    const int W = ctx->width, H = ctx->height;
+    const size_t fbBytes = (size_t)W * H * 4;
+    CU(ctx, cudaSetDevice(ctx->device));
+    uint32_t* out = (uint32_t*)dst;
+    if (!dst_is_device) {
+        if (!ctx->presentStage) {
+            cudaError_t e = cudaMalloc(&ctx->presentStage, fbBytes);
+            if (e != cudaSuccess) return fail(ctx, e == cudaErrorMemoryAllocation ? CVX_ERR_OUT_OF_MEMORY : CVX_ERR_CUDA, "present staging allocation failed: %s", cudaGetErrorString(e));
+        }
+        out = ctx->presentStage;
+    }
+    CU(ctx, cvxd_launch_present(current_target(ctx), out, W, H, format == CVX_PRESENT_BGRA8, top_down != 0, ctx->stream));
+    ctx->launches++;
+    if (!dst_is_device) {
+        CU(ctx, cudaMemcpyAsync(dst, out, fbBytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     return CVX_OK;
 }
 

@@ -1063,6 +1063,44 @@ phase2_kernel(const __grid_constant__ cvxd_blit p) {
     if (owned) p.frame[(int64_t)y * p.width + x] = color;
 }
 
+// ---- debug views: the shader's COPY_MAIN1 / COPY_MAIN2 variants (RayBufferBlit.shader:48-53) -----------------------
+// uv = SV_POSITION.xy / _ScreenParams.xy with the pixel centre measured from the TOP (D3D); the fragment
+// samples tex2D(buffer, float2(1 - uv.y, uv.x)), point filtered (RayBuffer.cs:32): texture x runs along a ray row
+// (rowLen texels), texture y over the rows. So screen x selects the ray row and screen y the pixel along it.
+__global__ void __launch_bounds__(256)
+raybuffer_view_kernel(const uint32_t* __restrict__ buf, int rows, int rowLen, uint32_t* __restrict__ frame, int width, int height) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= width || y >= height) return;
+    const float vx = (float)x + 0.5f, vy = (float)height - ((float)y + 0.5f); // SV_POSITION, y from the top
+    const float uvx = vx / (float)width, uvy = vy / (float)height;
+    const float tu = 1.0f - uvy, tv = uvx;
+    int col = f2i(floorf(tu * (float)rowLen)), row = f2i(floorf(tv * (float)rows));
+    col = max(0, min(rowLen - 1, col)); row = max(0, min(rows - 1, row)); // clamp addressing
+    frame[(int64_t)y * width + x] = __ldg(buf + (int64_t)row * rowLen + col);
+}
+
+// ---- presentation: ColorARGB32 frame (bytes a,r,g,b; row 0 = bottom) -> RGBA8 or BGRA8, optionally top-down ------------
+// One 128-bit load and store per thread (4 pixels); width is a multiple of 4 on this path, other widths take the scalar tail.
+__global__ void __launch_bounds__(256)
+present_kernel(const uint32_t* __restrict__ frame, uint32_t* __restrict__ out, int width, int height, int bgra, int topDown) {
+    const int quadsPerRow = (width + 3) >> 2;
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (int64_t)quadsPerRow * height) return;
+    const int y = (int)(q / quadsPerRow), x = (int)(q - (int64_t)y * quadsPerRow) * 4;
+    const uint32_t* src = frame + (int64_t)y * width + x;
+    uint32_t* dst = out + (int64_t)(topDown ? height - 1 - y : y) * width + x;
+    // [a,r,g,b] -> [r,g,b,a] is a byte rotation, -> [b,g,r,a] a byte reversal
+    const uint32_t sel = bgra ? 0x0123u : 0x0321u;
+    if (x + 3 < width && (width & 3) == 0) {
+        uint4 v = *reinterpret_cast<const uint4*>(src);
+        v.x = __byte_perm(v.x, 0u, sel); v.y = __byte_perm(v.y, 0u, sel); v.z = __byte_perm(v.z, 0u, sel); v.w = __byte_perm(v.w, 0u, sel);
+        *reinterpret_cast<uint4*>(dst) = v;
+    } else {
+        for (int i = 0; i < 4 && x + i < width; i++) dst[i] = __byte_perm(src[i], 0u, sel);
+    }
+}
+
 __global__ void ray_setup_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ cvxd_frame f, cvxd_ray_state* out, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1139,6 +1177,19 @@ cudaError_t cvxd_launch_ray_setup(const cvxd_world& world, const cvxd_frame& fra
 cudaError_t cvxd_launch_fill(uint32_t* dst, uint32_t value, int64_t n, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
     fill_kernel<<<148 * 8, 256, 0, stream>>>(dst, value, n);
+    return cudaGetLastError();
+}
+cudaError_t cvxd_launch_raybuffer_view(const uint32_t* buf, int rows, int row_len, uint32_t* frame, int width, int height, cudaStream_t stream) {
+    if (width <= 0 || height <= 0) return cudaSuccess;
+    dim3 grid((width + 31) / 32, (height + 7) / 8);
+    raybuffer_view_kernel<<<grid, 256, 0, stream>>>(buf, rows, row_len, frame, width, height);
+    return cudaGetLastError();
+}
+
+cudaError_t cvxd_launch_present(const uint32_t* frame, uint32_t* out, int width, int height, int bgra, int top_down, cudaStream_t stream) {
+    if (width <= 0 || height <= 0) return cudaSuccess;
+    const int64_t quads = (int64_t)((width + 3) >> 2) * height;
+    present_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, stream>>>(frame, out, width, height, bgra, top_down);
     return cudaGetLastError();
 }
 #endif /* !CVX_EMU */

@@ -573,4 +573,29 @@ int cvx_world_file_read(const char* path, int32_t out_dims[3], int32_t* out_worl
     return CVX_OK;
 }
 
+// Presentation helper: a ColorARGB32 frame (bytes a,r,g,b; row 0 = bottom) as an uncompressed 32-bit BMP. BMP rows are stored
+// bottom-up and its pixels are B,G,R,A bytes, so every pixel is the byte reversal of ours and rows keep their order.
+int cvx_host_write_bmp(const char* path, const void* argb_frame, int32_t width, int32_t height) {
+    if (!path || !argb_frame || width < 1 || height < 1) return CVX_ERR_INVALID_ARGUMENT;
+    FILE* f = fopen(path, "wb");
+    if (!f) return CVX_ERR_IO;
+    const uint32_t pixelBytes = (uint32_t)width * (uint32_t)height * 4u;
+    uint8_t hdr[54] = {0};
+    auto put32 = [&](int at, uint32_t v) { hdr[at] = (uint8_t)v; hdr[at + 1] = (uint8_t)(v >> 8); hdr[at + 2] = (uint8_t)(v >> 16); hdr[at + 3] = (uint8_t)(v >> 24); };
+    hdr[0] = 'B'; hdr[1] = 'M';
+    put32(2, 54u + pixelBytes); put32(10, 54u);
+    put32(14, 40u); put32(18, (uint32_t)width); put32(22, (uint32_t)height);
+    hdr[26] = 1; hdr[28] = 32;             // planes, bits per pixel; compression 0 = BI_RGB
+    put32(34, pixelBytes); put32(38, 2835u); put32(42, 2835u);
+    bool ok = fwrite(hdr, 1, 54, f) == 54;
+    std::vector<uint32_t> line((size_t)width);
+    const uint32_t* src = (const uint32_t*)argb_frame;
+    for (int y = 0; y < height && ok; y++) {
+        for (int x = 0; x < width; x++) line[(size_t)x] = __builtin_bswap32(src[(size_t)y * width + x]);
+        ok = fwrite(line.data(), 4, (size_t)width, f) == (size_t)width;
+    }
+    fclose(f);
+    return ok ? CVX_OK : CVX_ERR_IO;
+}
+
 } // extern "C"

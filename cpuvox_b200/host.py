@@ -268,6 +268,22 @@ class RenderManager:
     def clear_raybuffers(self, argb: int = 0):
         self._ck(lib.cvx_clear_raybuffers(self._ctx, argb))
 
+    def blit_raybuffer(self, which: int):
+        """Debug view of the last view's raybuffer (0 = top/down, 1 = left/right): the shader's COPY_MAIN1 / COPY_MAIN2 variants
+        (RayBufferBlit.shader:48-53), written into the framebuffer."""
+        self._ck(lib.cvx_blit_raybuffer(self._ctx, which))
+
+    def present(self, fmt: int = 0, top_down: bool = True, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """cvx_present to host memory: the frame as RGBA8 (fmt 0) or BGRA8 (fmt 1) bytes, rows top-down or bottom-up."""
+        if out is None:
+            out = np.empty((self.height, self.width, 4), dtype=np.uint8)
+        self._ck(lib.cvx_present(self._ctx, fmt, int(top_down), _ptr(out), 0))
+        return out
+
+    def present_device(self, device_ptr: int, fmt: int = 0, top_down: bool = True):
+        """cvx_present into a caller-owned W*H*4 device buffer (graphics interop resource, encoder surface), on the context's stream."""
+        self._ck(lib.cvx_present(self._ctx, fmt, int(top_down), C.c_void_p(device_ptr), 1))
+
     def counters(self, reset: bool = True) -> dict:
         c = N.Counters()
         self._ck(lib.cvx_get_counters(self._ctx, C.byref(c), int(reset)))
@@ -357,6 +373,12 @@ RAY_STATE_DTYPE = np.dtype([
     ("position", "<i4", 2), ("step", "<i4", 2), ("start", "<f4", 2), ("dir", "<f4", 2),
     ("t_delta", "<f4", 2), ("t_max", "<f4", 2), ("intersection_distances", "<f4", 2),
 ])
+
+
+def write_bmp(path: str, frame: np.ndarray) -> None:
+    """A frame as returned by read_frame (uint32 ColorARGB32, row 0 = bottom) as a 32-bit .bmp."""
+    frame = np.ascontiguousarray(frame, dtype=np.uint32)
+    check(lib.cvx_host_write_bmp(path.encode(), _ptr(frame), frame.shape[1], frame.shape[0]))
 
 
 def alloc_pinned(shape, dtype=np.uint32) -> np.ndarray:

@@ -125,6 +125,8 @@ SYMBOLS = {
     "cvx_read_raybuffer": (C.c_int, [_P, _I32, _P, _I64]),
     "cvx_get_counters": (C.c_int, [_P, C.POINTER(Counters), _I32]),
     "cvx_clear_raybuffers": (C.c_int, [_P, _U32]),
+    "cvx_blit_raybuffer": (C.c_int, [_P, _I32]),
+    "cvx_present": (C.c_int, [_P, _I32, _I32, _P, _I32]),
     "cvx_alloc_pinned": (C.c_int, [_I64, C.POINTER(_P)]),
     "cvx_free_pinned": (C.c_int, [_P]),
     "cvx_device_frame": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_I64)]),
@@ -155,6 +157,7 @@ SYMBOLS = {
     "cvx_builder_lod": (C.c_int, [_P, _I32, C.POINTER(_P), C.POINTER(_I64), C.POINTER(_I32), C.POINTER(_I64)]),
     "cvx_builder_free": (None, [_P]),
     "cvx_world_file_write": (C.c_int, [C.c_char_p, C.POINTER(_I32 * 3), _I32, C.POINTER(_P), C.POINTER(_I64)]),
+    "cvx_host_write_bmp": (C.c_int, [C.c_char_p, _P, _I32, _I32]),
     "cvx_world_file_read": (C.c_int, [C.c_char_p, C.POINTER(_I32 * 3), C.POINTER(_I32), C.POINTER(_P * LOD_LEVELS), C.POINTER(_I64 * LOD_LEVELS)]),
 }
 

@@ -62,6 +62,9 @@ public static unsafe class CpuVoxB200
 	[DllImport(LIB)] public static extern int cvx_read_raybuffer(IntPtr ctx, int which, void* dstArgb, long bytes);
 	[DllImport(LIB)] public static extern int cvx_get_counters(IntPtr ctx, out Counters counters, int reset);
 	[DllImport(LIB)] public static extern int cvx_device_frame(IntPtr ctx, out IntPtr devicePtr, out long bytes);
+	[DllImport(LIB)] public static extern int cvx_clear_raybuffers(IntPtr ctx, uint argb);
+	[DllImport(LIB)] public static extern int cvx_blit_raybuffer(IntPtr ctx, int which); // ERenderMode.RayBufferTopDown (0) / RayBufferLeftRight (1), UnityManager.cs:471-483
+	[DllImport(LIB)] public static extern int cvx_present(IntPtr ctx, int format, int topDown, void* dst, int dstIsDevice); // 0 = RGBA8, 1 = BGRA8
 
 	public static void Check (int code, IntPtr ctx)
 	{

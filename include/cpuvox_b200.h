@@ -137,6 +137,18 @@ int cvx_read_raybuffer(cvx_ctx* ctx, int32_t which, void* dst_argb, int64_t byte
 int cvx_get_counters(cvx_ctx* ctx, cvx_counters* out, int32_t reset);
 /* Debug: fill both raybuffers with one colour (RenderManager.ClearRayBuffer, RenderManager.cs:58-92 uses magenta). */
 int cvx_clear_raybuffers(cvx_ctx* ctx, uint32_t argb);
+/* Debug views, the shader's COPY_MAIN1 / COPY_MAIN2 variants (RayBufferBlit.shader:48-53; UnityManager.ERenderMode.RayBufferTopDown /
+ * RayBufferLeftRight, UnityManager.cs:129-134,471-483): write the whole raybuffer `which` (0 = top/down, 1 = left/right) of the last
+ * view into the framebuffer, stretched over the screen — screen x selects the ray row, screen y the pixel along the row, point
+ * sampled. Use with cvx_clear_raybuffers(magenta) before the draw to see which pixels a frame wrote. */
+int cvx_blit_raybuffer(cvx_ctx* ctx, int32_t which);
+/* Presentation, the step after the path (replaces Unity's camera target): convert the framebuffer (ColorARGB32, row 0 = bottom) on
+ * the device to RGBA8 or BGRA8 bytes, rows top-down (top_down != 0: what swap chains, image files and encoders take) or bottom-up,
+ * into `dst`: a W*H*4 device buffer (dst_is_device != 0; e.g. a mapped graphics-interop resource or an encoder surface; ordered on
+ * the context's stream) or host memory (the call returns when the copy has landed). */
+#define CVX_PRESENT_RGBA8 0
+#define CVX_PRESENT_BGRA8 1
+int cvx_present(cvx_ctx* ctx, int32_t format, int32_t top_down, void* dst, int32_t dst_is_device);
 /* Page-locked host memory for asynchronous frame readback (cvx_draw_batch, cvx_read_frame). */
 int cvx_alloc_pinned(int64_t bytes, void** out);
 int cvx_free_pinned(void* p);
@@ -267,6 +279,10 @@ int cvx_world_file_write(const char* path, const int32_t dims[3], int32_t world_
 /* Reads header + table; blobs are malloc'ed (free each with cvx_host_free). */
 int cvx_world_file_read(const char* path, int32_t out_dims[3], int32_t* out_world_count,
                         void** out_blobs /* [CVX_LOD_LEVELS] */, int64_t* out_blob_bytes /* [CVX_LOD_LEVELS] */);
+
+/* Write a ColorARGB32 frame (as returned by cvx_read_frame: row 0 = bottom) as an uncompressed 32-bit .bmp (bottom-up BGRA,
+ * so rows are stored in the order they arrive). Host only. */
+int cvx_host_write_bmp(const char* path, const void* argb_frame, int32_t width, int32_t height);
 
 #ifdef __cplusplus
 }

@@ -1207,4 +1207,25 @@ int orc_blit(const orc_frame_setup* s, int32_t W, int32_t H, const uint32_t* td,
     return 0;
 }
 
+/*
+ * Debug views: RayBufferBlit.shader frag, COPY_MAIN1 / COPY_MAIN2 variants (Shaders/RayBufferBlit.shader:48-53):
+ *   uv = SV_POSITION.xy / _ScreenParams.xy  (pixel centre, y from the TOP: D3D)
+ *   return tex2D(buffer, float2(1 - uv.y, uv.x))   point filtered (RayBuffer.cs:32), clamp addressing
+ * Texture x runs along one ray row (row_len texels), texture y over the ray rows. Frame rows are bottom-up like orc_blit's.
+ */
+int orc_blit_raybuffer(const uint32_t* buf, int32_t rows, int32_t row_len, int32_t W, int32_t H, uint32_t* frame) {
+    if (!buf || !frame || rows < 1 || row_len < 1 || W < 1 || H < 1) return -1;
+    for (int y = 0; y < H; y++) {
+        for (int x = 0; x < W; x++) {
+            float vx = (float)x + 0.5f, vy = (float)H - ((float)y + 0.5f);
+            float uvx = vx / (float)W, uvy = vy / (float)H;
+            float tu = 1.0f - uvy, tv = uvx;
+            int col = i_clamp(f2i(floorf(tu * (float)row_len)), 0, row_len - 1);
+            int row = i_clamp(f2i(floorf(tv * (float)rows)), 0, rows - 1);
+            frame[(int64_t)y * W + x] = buf[(int64_t)row * row_len + col];
+        }
+    }
+    return 0;
+}
+
 } // extern "C"

@@ -102,6 +102,8 @@ int orc_render_raybuffers(const orc_world* w, const orc_frame_setup* setup, int3
 /* Phase 2: RayBufferBlit.shader default variant, restated per pixel. frame: W*H, row 0 = bottom. */
 int orc_blit(const orc_frame_setup* setup, int32_t width, int32_t height, const uint32_t* td,
              const uint32_t* lr, uint32_t* frame, int32_t row_begin, int32_t row_end, int32_t n_threads);
+/* Debug views COPY_MAIN1 / COPY_MAIN2 of the blit shader (RayBufferBlit.shader:48-53): raybuffer `buf` (rows x row_len) stretched over the screen. */
+int orc_blit_raybuffer(const uint32_t* buf, int32_t rows, int32_t row_len, int32_t width, int32_t height, uint32_t* frame);
 /* Per-ray state after the three setup jobs (DrawSegmentRayJob.cs:12-144). */
 int orc_ray_setup(const orc_world* w, const orc_frame_setup* setup, int32_t width, int32_t height,
                   orc_ray_state* out, int32_t max_rays);

@@ -77,6 +77,8 @@ def lib():
         L.orc_benchmark_pose.argtypes = [C.c_float, C.POINTER(C.c_int32 * 3), C.POINTER(Pose)]
         L.orc_render_raybuffers.argtypes = [P, C.POINTER(FrameSetup), C.c_int32, C.c_int32, P, P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Counters)]
         L.orc_blit.argtypes = [C.POINTER(FrameSetup), C.c_int32, C.c_int32, P, P, P, C.c_int32, C.c_int32, C.c_int32]
+        L.orc_blit_raybuffer.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P]
+        L.orc_blit_raybuffer.restype = C.c_int
         L.orc_ray_setup.argtypes = [P, C.POINTER(FrameSetup), C.c_int32, C.c_int32, P, C.c_int32]
         L.orc_ray_stats.argtypes = [P, C.POINTER(FrameSetup), C.c_int32, C.c_int32, P, C.c_int32]
         L.orc_dda_walk.argtypes = [C.POINTER(C.c_float * 2), C.POINTER(C.c_float * 2), C.POINTER(C.c_float * LODS), C.c_float, C.c_int32, P, P]
@@ -161,6 +163,15 @@ def blit(setup: FrameSetup, width, height, td, lr, threads=0, row_begin=0, row_e
         frame = np.zeros((height, width), dtype=np.uint32)
     r = lib().orc_blit(C.byref(setup), width, height, td.ctypes.data_as(C.c_void_p), lr.ctypes.data_as(C.c_void_p),
                        frame.ctypes.data_as(C.c_void_p), row_begin, row_end, threads)
+    assert r == 0
+    return frame
+
+
+def blit_raybuffer(buf: np.ndarray, width, height) -> np.ndarray:
+    """Debug view COPY_MAIN1 / COPY_MAIN2 (RayBufferBlit.shader:48-53) of one raybuffer (rows x row_len)."""
+    buf = np.ascontiguousarray(buf, dtype=np.uint32)
+    frame = np.zeros((height, width), dtype=np.uint32)
+    r = lib().orc_blit_raybuffer(buf.ctypes.data_as(C.c_void_p), buf.shape[0], buf.shape[1], width, height, frame.ctypes.data_as(C.c_void_p))
     assert r == 0
     return frame
 

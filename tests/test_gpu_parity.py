@@ -259,6 +259,47 @@ def test_tall_columns_near_plane_and_irregular_worlds(cv, orc, rm):
         _assert_same(_gpu_frame(rm, s, MAGENTA), _oracle_frame(orc, ow, s, W, H, MAGENTA), f"irregular {pos} {eul}")
 
 
+def test_debug_views_and_presentation(cv, orc, rm, mill_world, tmp_path):
+    """f4: the shader's COPY_MAIN1 / COPY_MAIN2 debug views (RayBufferBlit.shader:48-53) against the oracle's restatement, after
+    the magenta clear the reference uses (RenderManager.cs:58-92); cvx_present against numpy byte shuffles; the .bmp writer."""
+    rm.upload_world(mill_world)
+    for (W, H) in ((320, 180), (333, 217)):
+        rm.set_resolution(W, H)
+        s = rm.make_setup(pose_for(cv, mill_world, POSES[0]))
+        rm.clear_raybuffers(MAGENTA)
+        rm.draw_setup(s)
+        rm.sync()
+        frame = rm.read_frame()
+        td, lr = rm.read_raybuffers()
+        for which, buf in ((0, td), (1, lr)):
+            rm.blit_raybuffer(which)
+            rm.sync()
+            got = rm.read_frame()
+            want = orc.blit_raybuffer(buf, W, H)
+            assert np.array_equal(got, want), f"debug view {which} at {W}x{H}"
+            assert (got == MAGENTA).any() and (got != MAGENTA).any()   # untouched rows/pixels stay magenta, written ones do not
+        rm.draw_setup(s)   # back to the normal frame
+        rm.sync()
+        assert np.array_equal(rm.read_frame(), frame)
+        b = frame.view(np.uint8).reshape(H, W, 4)   # bytes a, r, g, b
+        rgba = np.stack([b[..., 1], b[..., 2], b[..., 3], b[..., 0]], axis=-1)
+        bgra = np.stack([b[..., 3], b[..., 2], b[..., 1], b[..., 0]], axis=-1)
+        assert np.array_equal(rm.present(0, top_down=False), rgba)
+        assert np.array_equal(rm.present(0, top_down=True), rgba[::-1])
+        assert np.array_equal(rm.present(1, top_down=True), bgra[::-1])
+        assert np.array_equal(rm.present(1, top_down=False), bgra)
+    # device destination: a torch buffer stands in for a mapped graphics resource
+    import torch
+    dst = torch.zeros(H * W, dtype=torch.int32, device="cuda:0")
+    rm.present_device(dst.data_ptr(), 0, True)
+    rm.sync()
+    assert np.array_equal(dst.cpu().numpy().view(np.uint8).reshape(H, W, 4), rgba[::-1])
+    with pytest.raises(cv.CvxError):
+        rm.present(7)
+    with pytest.raises(cv.CvxError):
+        rm.blit_raybuffer(2)
+
+
 def test_error_paths(cv):
     from cpuvox_b200 import native as N
     m = cv.RenderManager(0)

@@ -110,6 +110,37 @@ def test_limit_rotation_horizon(cv):
     assert total == W  # one clamped segment spanning the screen width
 
 
+def test_write_bmp_round_trip(cv, tmp_path):
+    """cvx_host_write_bmp: 54-byte header, bottom-up BGRA rows = our row order with every pixel byte-reversed."""
+    rng = np.random.default_rng(3)
+    W, H = 37, 11
+    frame = rng.integers(0, 2**32, size=(H, W), dtype=np.uint64).astype(np.uint32)
+    path = str(tmp_path / "f.bmp")
+    cv.write_bmp(path, frame)
+    raw = np.fromfile(path, dtype=np.uint8)
+    assert raw[:2].tobytes() == b"BM" and raw.size == 54 + W * H * 4
+    assert int(raw[2:6].view(np.uint32)[0]) == raw.size and int(raw[10:14].view(np.uint32)[0]) == 54
+    assert int(raw[18:22].view(np.int32)[0]) == W and int(raw[22:26].view(np.int32)[0]) == H and int(raw[28:30].view(np.uint16)[0]) == 32
+    px = raw[54:].reshape(H, W, 4)                   # b, g, r, a
+    ours = frame.view(np.uint8).reshape(H, W, 4)     # a, r, g, b
+    assert np.array_equal(px, ours[..., ::-1])
+
+
+def test_oracle_debug_view_hand_case(orc):
+    """COPY_MAIN1/2 restatement (RayBufferBlit.shader:48-53): screen x picks the ray row, screen y (bottom-up) the pixel along it."""
+    rows, row_len, W, H = 6, 4, 3, 2
+    buf = (np.arange(rows * row_len, dtype=np.uint32) + 1).reshape(rows, row_len)
+    fr = orc.blit_raybuffer(buf, W, H)
+    for y in range(H):
+        for x in range(W):
+            u = 1.0 - (H - (y + 0.5)) / H      # = (y + 0.5) / H
+            v = (x + 0.5) / W
+            assert fr[y, x] == buf[int(v * rows), int(u * row_len)]
+    # identity-sized view: a raybuffer with as many rows as screen columns and row_len == H shows up transposed
+    buf = np.arange(5 * 7, dtype=np.uint32).reshape(5, 7)
+    assert np.array_equal(orc.blit_raybuffer(buf, 5, 7), buf.T)
+
+
 def test_algorithmic_bytes_formula(cv):
     c = {"dda_steps": 10, "runs_visited": 20, "px_voxel": 30, "px_sky": 40}
     assert cv.algorithmic_bytes(c, 8, 4) == 12 * 10 + 4 * 20 + 4 * 30 + 4 * 70 + 8 * 32

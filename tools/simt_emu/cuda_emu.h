@@ -136,6 +136,12 @@ template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline int __ffs(unsigned x) { return x ? __builtin_ctz(x) + 1 : 0; }
 static inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) { // prmt.b32, default mode: nibble i of sel picks a byte of {b,a}
+    const unsigned long long pool = ((unsigned long long)b << 32) | a;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) r |= (unsigned)((pool >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
+}
 static inline int __float2int_rz(float f) { // cvt.rzi.s32.f32: saturating, NaN -> 0
     if (f != f) return 0;
     if (f >= 2147483648.0f) return INT_MAX;
