@@ -8,8 +8,10 @@
 
 #define CVXD_LODS 6
 #define CVXD_MAX_AXIS 8192          /* longest raybuffer row (max(W,H)) the seen-mask in shared memory supports */
+#ifndef CVXD_THREADS_PER_CTA
 #define CVXD_THREADS_PER_CTA 128
-#define CVXD_TIMING_REGIONS 8
+#endif
+#define CVXD_TIMING_REGIONS 16
 
 /* Device copy of one World LOD (Assets/Code/World.cs:8-43,161-188), transcoded on the host at upload (world_transcode.h):
  *   headers   one 16-byte aligned uint4 per column, fetched by a lane with a single 128-bit load:

@@ -364,7 +364,7 @@ __device__ __forceinline__ void touch(const uint32_t* p) {
 #ifndef CVXD_MIN_CTAS_PER_SM
 #define CVXD_MIN_CTAS_PER_SM 4
 #endif
-template <int G, bool COUNTERS, bool TIMING, bool FAST>
+template <int G, bool COUNTERS, bool TIMING, bool FAST, bool INV>
 __global__ void __launch_bounds__(CVXD_THREADS_PER_CTA, CVXD_MIN_CTAS_PER_SM)
 phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ cvxd_frame f) {
 #ifdef CVX_EMU
@@ -385,7 +385,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
 #define GSHFL(v, src) __shfl_sync(gmask, (v), (src), G)
 
     // TIMING builds (cvx_debug_ray_timing): cycles per code region of this ray, STAMP(r) closes the current region
-    long long tAcc[CVXD_TIMING_REGIONS] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tAcc[CVXD_TIMING_REGIONS] = {0};
     long long tPrev = TIMING ? clock64() : 0;
     int tCur = 0;
 #define STAMP(r) do { if (TIMING) { const long long t_ = clock64(); tAcc[tCur] += t_ - tPrev; tPrev = t_; tCur = (r); } } while (0)
@@ -426,7 +426,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
         const float worldMaxY = (float)world.dim_y;
         const float camY = f.pos_y;
         const float cameraPosYNormalized = camY / worldMaxY;
-        const int ITER = f.inverse ? -1 : 1; // RenderJob.Execute :174-178
+        constexpr int ITER = INV ? -1 : 1; // RenderJob.Execute :174-178 (INV = InverseElementIterationDirection, one kernel instance per direction)
         const float EPS = float_epsilon();
         float frustumDirMaxWorld = EPS, frustumDirMinWorld = EPS;
 
@@ -915,15 +915,19 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                         if (isCap) candC &= candC - 1u; else candS &= candS - 1u;
                         int bMin = GSHFL(isCap ? r_cMin : r_sMin, j), bMax = GSHFL(isCap ? r_cMax : r_sMax, j);
                         EMU_STAT(5); // commit candidates examined
-                        if (!span_would_write(rw, bMin, bMax)) continue; // written over / cut off since the round was formed
+                        STAMP(8);
+                        if (!span_would_write(rw, bMin, bMax)) { STAMP(6); continue; } // written over / cut off since the round was formed
                         EMU_STAT(6); // spans committed (each writes at least one pixel)
                         if (isCap) EMU_STAT(7);
+                        STAMP(9);
                         reduce_pixel_horizon(rw, bMin, bMax); // :507-517 / :583-593
+                        STAMP(10);
                         if (isCap) {
                             const uint32_t color = FAST ? GSHFL(r_capColor, j) : cache[7 * G + j];
                             for (int y = bMin + gl; y <= bMax; y += G) // :595-602
                                 if (!((rw.seen[y >> 5] >> (y & 31)) & 1u)) row[y] = color;
                         } else {
+                            STAMP(11);
                             float jbfx, jbfy, jAx, jAy, jBx, jBy;
                             int jLen;
                             const int jCi = GSHFL(r_ci, j);
@@ -953,6 +957,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                                 jBx = __uint_as_float(cache[4 * G + j]); jBy = __uint_as_float(cache[5 * G + j]);
                                 jLen = (int)cache[6 * G + j];
                             }
+                            STAMP(12);
                             for (int y = bMin + gl; y <= bMax; y += G) { // :519-533
                                 if (!((rw.seen[y >> 5] >> (y & 31)) & 1u)) {
                                     int idx = jCi;
@@ -967,9 +972,11 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                                 }
                             }
                         }
+                        STAMP(13);
                         __syncwarp(gmask);
                         { const int fresh = mark_seen<G>(rw.seen, rw.full, bMin, bMax, gl); if (COUNTERS) acc.px_voxel += fresh; }
                         __syncwarp(gmask);
+                        STAMP(6);
                         frustumDirMaxWorld = EPS; // a pixel was written (:522,598)
                         if (rw.nf_min > rw.nf_max) { terminated = true; visitedHere = j + 1 - base; break; } // :535-539,604-608
                     }
@@ -1132,18 +1139,16 @@ static cudaError_t launch_phase1_g(const cvxd_world& world, const cvxd_frame& fr
     const size_t smem = (size_t)groupsPerCta * (seenWords + ((seenWords + 31) >> 5) + 9 * G) * sizeof(uint32_t);
     // FAST: the boundary-table kernel, for regular worlds (world_transcode.h)
     const bool fast = world.regular && !frame.general_path;
+#define CVXD_P1(C, T, F) do { \
+        if (frame.inverse) phase1_kernel<G, C, T, F, true><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame); \
+        else               phase1_kernel<G, C, T, F, false><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame); } while (0)
     if (frame.timing) {
-        if (G != 32) return cudaErrorInvalidValue; // the timing build exists for the default group width only
-        if (fast) phase1_kernel<32, false, true, true><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
-        else      phase1_kernel<32, false, true, false><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
+        if constexpr (G != 32) return cudaErrorInvalidValue; // the timing build exists for the default group width only
+        else { if (fast) CVXD_P1(false, true, true); else CVXD_P1(false, true, false); }
     }
-    else if (frame.counters) {
-        if (fast) phase1_kernel<G, true, false, true><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
-        else      phase1_kernel<G, true, false, false><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
-    } else {
-        if (fast) phase1_kernel<G, false, false, true><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
-        else      phase1_kernel<G, false, false, false><<<blocks, CVXD_THREADS_PER_CTA, smem, stream>>>(world, frame);
-    }
+    else if (frame.counters) { if (fast) CVXD_P1(true, false, true); else CVXD_P1(true, false, false); }
+    else { if (fast) CVXD_P1(false, false, true); else CVXD_P1(false, false, false); }
+#undef CVXD_P1
     return cudaGetLastError();
 }
 

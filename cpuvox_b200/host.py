@@ -335,9 +335,9 @@ class RenderManager:
         return np.frombuffer(out, dtype=RAY_STATE_DTYPE, count=total).copy()
 
     def ray_timing(self, setup: FrameSetup) -> np.ndarray:
-        """Debug: cycles per code region per ray, shape (rays, 8) — see cvx_debug_ray_timing."""
+        """Debug: cycles per code region per ray, shape (rays, 16) — see cvx_debug_ray_timing."""
         total = sum(max(0, setup.segments[k].ray_count) for k in range(4))
-        out = np.zeros((max(1, total), 8), dtype=np.int64)
+        out = np.zeros((max(1, total), 16), dtype=np.int64)
         self._ck(lib.cvx_debug_ray_timing(self._ctx, C.byref(setup), _ptr(out), total))
         return out[:total]
 

@@ -212,8 +212,10 @@ typedef struct cvx_ray_state {
 int cvx_debug_ray_setup(cvx_ctx* ctx, const cvx_frame_setup* setup, cvx_ray_state* out, int32_t max_rays);
 /* Debug: run Phase 1 once with per-ray cycle counters; CVX_TIMING_REGIONS int64 per flat ray index:
  * 0 setup/other, 1 DDA look-ahead + header fetch, 2 column selection (frustum cull), 3 frustum re-narrowing,
- * 4 run fetch + bounds, 5 span geometry, 6 span commit, 7 skybox fill. Returns the frame's ray count. */
-#define CVX_TIMING_REGIONS 8
+ * 4 run fetch + bounds, 5 span geometry, 6 column resolve + commit-loop control, 7 skybox fill, 8 commit re-test (span_would_write),
+ * 9 ReducePixelHorizon, 10 cap pixels, 11 side-span perspective setup, 12 side pixels, 13 written-mask update, 14-15 unused.
+ * Returns the frame's ray count. */
+#define CVX_TIMING_REGIONS 16
 int cvx_debug_ray_timing(cvx_ctx* ctx, const cvx_frame_setup* setup, int64_t* out_cycles, int32_t max_rays);
 
 /* =============================================================================================

@@ -25,16 +25,21 @@ namespace {
 
 struct LaunchArgs { const cvxd_world* world; const cvxd_frame* frame; int variant, group; bool counters; };
 
+template <int G, bool INV>
+void body_gi(const LaunchArgs* a) {
+    if (a->variant == 0) {
+        if (a->counters) phase1_kernel<G, true, false, false, INV>(*a->world, *a->frame);
+        else phase1_kernel<G, false, false, false, INV>(*a->world, *a->frame);
+    } else {
+        if (a->counters) phase1_kernel<G, true, false, true, INV>(*a->world, *a->frame);
+        else phase1_kernel<G, false, false, true, INV>(*a->world, *a->frame);
+    }
+}
+
 template <int G>
 void body_g(void* p) {
     const LaunchArgs* a = (const LaunchArgs*)p;
-    if (a->variant == 0) {
-        if (a->counters) phase1_kernel<G, true, false, false>(*a->world, *a->frame);
-        else phase1_kernel<G, false, false, false>(*a->world, *a->frame);
-    } else {
-        if (a->counters) phase1_kernel<G, true, false, true>(*a->world, *a->frame);
-        else phase1_kernel<G, false, false, true>(*a->world, *a->frame);
-    }
+    if (a->frame->inverse) body_gi<G, true>(a); else body_gi<G, false>(a);
 }
 
 } // namespace
