@@ -18,6 +18,7 @@
 #include "device_types.h"
 #include "host_frame.h"
 #include "world_transcode.h"
+#include "world_builder.h"
 
 static_assert(sizeof(cvx_ray_state) == sizeof(cvxd_ray_state), "ray state layout");
 static_assert(sizeof(cvx_counters) == sizeof(cvxd_counters), "counter layout");
@@ -513,6 +514,29 @@ int cvx_present(cvx_ctx* ctx, int32_t format, int32_t top_down, void* dst, int32
         CU(ctx, cudaMemcpyAsync(dst, out, fbBytes, cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    return CVX_OK;
+}
+
+// World production on the device (world_builder_gpu.cu): same inputs and the same blobs, byte for byte, as cvx_builder_from_mesh +
+// cvx_builder_lod(0 .. n_lods-1), i.e. WorldBuilder.Import -> ToLOD0World -> World.DownSample (UnityManager.cs:297-331).
+int cvx_gpu_builder_from_mesh(cvx_ctx* ctx, const float* positions, const uint8_t* colors32, int32_t n_vertices, int32_t max_dimension,
+                              const int32_t flips[3], int32_t n_lods, cvx_world_builder** out) {
+    if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
+    if (!positions || !colors32 || n_vertices < 3 || max_dimension < 1 || n_lods < 1 || n_lods > CVX_LOD_LEVELS || !out)
+        return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "bad mesh arguments");
+    *out = nullptr;
+    std::vector<float> xyz;
+    int dims[3];
+    int r = cvxh_remap_mesh(positions, n_vertices, max_dimension, flips, xyz, dims);
+    if (r) return fail(ctx, r, "mesh cannot be remapped to max dimension %d", max_dimension);
+    cvx_world_builder* b = new (std::nothrow) cvx_world_builder();
+    if (!b) return fail(ctx, CVX_ERR_OUT_OF_MEMORY, "out of host memory");
+    b->dims[0] = dims[0]; b->dims[1] = dims[1]; b->dims[2] = dims[2];
+    b->deviceBuilt = true;
+    std::string err;
+    r = cvxd_build_world_gpu(ctx->device, ctx->stream, xyz.data(), colors32, n_vertices, n_lods, b, &ctx->launches, err);
+    if (r) { cvx_builder_free(b); return fail(ctx, r, "device world build failed: %s", err.c_str()); }
+    *out = b;
     return CVX_OK;
 }
 

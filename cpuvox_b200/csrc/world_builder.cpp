@@ -16,6 +16,7 @@
  * deterministic element layout (columns allocated in index order, independent of thread count).
  */
 #include "../../include/cpuvox_b200.h"
+#include "world_builder.h"
 
 #include <algorithm>
 #include <atomic>
@@ -29,19 +30,14 @@
 
 namespace {
 
+using Blob = cvx_lod_blob;
+
 struct ColHeader { // World.RLEColumn, 12 bytes
     int32_t offset;
     uint16_t runCount, worldMin, worldMax, pad;
 };
 struct Run { int16_t colorsIndex, length; }; // World.RLEElement
 static_assert(sizeof(ColHeader) == 12 && sizeof(Run) == 4, "layout");
-
-struct Blob {
-    std::vector<uint8_t> bytes;
-    int columnCount = 0;
-    int64_t voxelCount = 0;
-    bool built = false;
-};
 
 template <class F>
 void run_parallel(int64_t n, int n_threads, F fn) {
@@ -154,7 +150,6 @@ void assemble_blob(Blob& blob, int columnCount, int64_t slots, const std::vector
     blob.built = true;
 }
 
-struct MeshVoxel { int32_t xz; int16_t y; uint32_t argb; };
 
 inline uint8_t to_byte(float c) { // Color -> Color32: round(clamp01(c)*255), half-to-even
     float v = c < 0.0f ? 0.0f : (c > 1.0f ? 1.0f : c);
@@ -221,22 +216,6 @@ inline uint32_t hash32(uint32_t x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 1
 inline float hash01(uint32_t x) { return (hash32(x) >> 8) * (1.0f / 16777216.0f); }
 
 } // namespace
-
-struct cvx_world_builder {
-    int dims[3] = {0, 0, 0};
-    int nThreads = 0;
-    Blob lods[CVX_LOD_LEVELS];
-    // mesh path: voxels binned by column (CSR)
-    std::vector<int64_t> colStart;
-    std::vector<MeshVoxel> voxels;
-    // synthetic path: kind + seed; columns generated on the fly
-    int synthKind = -1;
-    uint32_t seed = 0;
-    std::vector<uint16_t> height; // kind 0: heightmap
-    struct Box { int x0, x1, y0, y1, z0, z1; uint32_t color; int kind; }; // kind 1 objects
-    std::vector<Box> boxes;
-    std::vector<std::vector<int>> boxBins; int binShift = 6, binsX = 0, binsZ = 0;
-};
 
 namespace {
 
@@ -379,6 +358,7 @@ void emit_downsampled(const Blob& lod0, int dimY, int dimZ, int x, int z, int ne
 int build_lod(cvx_world_builder* b, int lod) {
     Blob& blob = b->lods[lod];
     if (blob.built) return CVX_OK;
+    if (b->deviceBuilt) return CVX_ERR_INVALID_ARGUMENT; // a device-built world holds exactly the LODs it was asked for
     if (lod > 0 && !b->lods[0].built) { int r = build_lod(b, 0); if (r) return r; }
     const int X = b->dims[0], Y = b->dims[1], Z = b->dims[2];
     const int cx = X >> lod, cz = Z >> lod;
@@ -413,6 +393,30 @@ int build_lod(cvx_world_builder* b, int lod) {
 }
 
 } // namespace
+
+int cvxh_remap_mesh(const float* positions, int32_t n_vertices, int32_t max_dimension, const int32_t flips[3],
+                    std::vector<float>& out_xyz, int dims[3]) {
+    if (!positions || n_vertices < 3 || max_dimension < 1) return CVX_ERR_INVALID_ARGUMENT;
+    std::vector<V3> v((size_t)n_vertices);
+    for (int i = 0; i < n_vertices; i++) v[i] = {positions[3 * i], positions[3 * i + 1], positions[3 * i + 2]};
+    // SimpleMesh.Remap_Internal, SimpleMesh.cs:64-106
+    V3 mn = v[0], mx = v[0];
+    for (int i = 1; i < n_vertices; i++) {
+        mn = {std::min(v[i].x, mn.x), std::min(v[i].y, mn.y), std::min(v[i].z, mn.z)};
+        mx = {std::max(v[i].x, mx.x), std::max(v[i].y, mx.y), std::max(v[i].z, mx.z)};
+    }
+    V3 size = mx - mn;
+    float scale = (float)max_dimension / std::max(size.x, std::max(size.y, size.z));
+    dims[0] = next_pow2((int)(size.x * scale)); dims[1] = next_pow2((int)(size.y * scale)); dims[2] = next_pow2((int)(size.z * scale));
+    for (auto& p : v) p = (p - mn) * scale;
+    if (flips && flips[0]) for (auto& p : v) p.x = (float)dims[0] - p.x;
+    if (flips && flips[1]) for (auto& p : v) p.y = (float)dims[1] - p.y;
+    if (flips && flips[2]) for (auto& p : v) p.z = (float)dims[2] - p.z;
+    if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1 || dims[1] > 32768) return CVX_ERR_INVALID_ARGUMENT;
+    out_xyz.resize(3 * (size_t)n_vertices);
+    for (int i = 0; i < n_vertices; i++) { out_xyz[3 * (size_t)i] = v[i].x; out_xyz[3 * (size_t)i + 1] = v[i].y; out_xyz[3 * (size_t)i + 2] = v[i].z; }
+    return CVX_OK;
+}
 
 extern "C" {
 
@@ -463,22 +467,12 @@ int cvx_obj_parse(const char* path, int32_t swap_yz, float** out_positions, uint
 int cvx_builder_from_mesh(const float* positions, const uint8_t* colors32, int32_t n_vertices, int32_t max_dimension,
                           const int32_t flips[3], int32_t n_threads, cvx_world_builder** out) {
     if (!positions || !colors32 || n_vertices < 3 || max_dimension < 1 || !out) return CVX_ERR_INVALID_ARGUMENT;
+    std::vector<float> xyz;
+    int dims[3];
+    int rr = cvxh_remap_mesh(positions, n_vertices, max_dimension, flips, xyz, dims);
+    if (rr) return rr;
     std::vector<V3> v((size_t)n_vertices);
-    for (int i = 0; i < n_vertices; i++) v[i] = {positions[3 * i], positions[3 * i + 1], positions[3 * i + 2]};
-    // SimpleMesh.Remap_Internal, SimpleMesh.cs:64-106
-    V3 mn = v[0], mx = v[0];
-    for (int i = 1; i < n_vertices; i++) {
-        mn = {std::min(v[i].x, mn.x), std::min(v[i].y, mn.y), std::min(v[i].z, mn.z)};
-        mx = {std::max(v[i].x, mx.x), std::max(v[i].y, mx.y), std::max(v[i].z, mx.z)};
-    }
-    V3 size = mx - mn;
-    float scale = (float)max_dimension / std::max(size.x, std::max(size.y, size.z));
-    int dims[3] = {next_pow2((int)(size.x * scale)), next_pow2((int)(size.y * scale)), next_pow2((int)(size.z * scale))};
-    for (auto& p : v) p = (p - mn) * scale;
-    if (flips && flips[0]) for (auto& p : v) p.x = (float)dims[0] - p.x;
-    if (flips && flips[1]) for (auto& p : v) p.y = (float)dims[1] - p.y;
-    if (flips && flips[2]) for (auto& p : v) p.z = (float)dims[2] - p.z;
-    if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1 || dims[1] > 32768) return CVX_ERR_INVALID_ARGUMENT;
+    for (int i = 0; i < n_vertices; i++) v[i] = {xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2]};
 
     cvx_world_builder* b = new cvx_world_builder();
     b->dims[0] = dims[0]; b->dims[1] = dims[1]; b->dims[2] = dims[2];

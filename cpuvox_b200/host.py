@@ -211,6 +211,31 @@ class RenderManager:
         if self.world is not None and self.width > 0:
             self.lod_distances = setup_lods(self.world.max_dimension, self.width, self.height, self.fov_y_degrees, self.lod_error)
 
+    def build_world_from_mesh(self, positions: np.ndarray, colors32: np.ndarray, max_dimension: int,
+                              flips: Sequence[bool] = (False, False, False), lods: int = LOD_LEVELS) -> World:
+        """World production on this context's GPU (cvx_gpu_builder_from_mesh): voxelizer + RLE + LOD mips as CUDA kernels; the
+        blobs equal World.from_mesh's byte for byte. The world is returned to the host (upload it with upload_world)."""
+        positions = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        colors32 = np.ascontiguousarray(colors32, dtype=np.uint8).reshape(-1, 4)
+        fl = (C.c_int32 * 3)(*[int(bool(f)) for f in flips])
+        b = C.c_void_p()
+        self._ck(lib.cvx_gpu_builder_from_mesh(self._ctx, _ptr(positions), _ptr(colors32), positions.shape[0], max_dimension, C.byref(fl), lods, C.byref(b)))
+        return World._from_builder(b, lods)
+
+    def build_world_from_obj(self, path: str, max_dimension: int = 1024, flips: Sequence[bool] = (True, False, False),
+                             swap_yz: bool = False, lods: int = LOD_LEVELS) -> World:
+        """ObjModel.Import on the host, then the conversion pipeline of UnityManager.cs:297-331 on the GPU."""
+        pos, col, n = C.c_void_p(), C.c_void_p(), C.c_int32()
+        check(lib.cvx_obj_parse(path.encode(), int(swap_yz), C.byref(pos), C.byref(col), C.byref(n)))
+        try:
+            fl = (C.c_int32 * 3)(*[int(bool(f)) for f in flips])
+            b = C.c_void_p()
+            self._ck(lib.cvx_gpu_builder_from_mesh(self._ctx, pos, col, n.value, max_dimension, C.byref(fl), lods, C.byref(b)))
+        finally:
+            lib.cvx_host_free(pos)
+            lib.cvx_host_free(col)
+        return World._from_builder(b, lods)
+
     # -- resolution -------------------------------------------------------------------------------
     def set_resolution(self, width: int, height: int) -> bool:  # RenderManager.SetResolution :94-109
         if width == self.width and height == self.height:

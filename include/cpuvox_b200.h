@@ -260,6 +260,13 @@ typedef struct cvx_world_builder cvx_world_builder;
 int cvx_builder_from_mesh(const float* positions, const uint8_t* colors32, int32_t n_vertices,
                           int32_t max_dimension, const int32_t flips[3], int32_t n_threads,
                           cvx_world_builder** out);
+/* The same world production on the device: triangles are voxelized, merged per (column, y), run-length encoded and
+ * downsampled into n_lods LODs by CUDA kernels on the context's GPU; the builder then holds blobs identical, byte for byte, to what
+ * cvx_builder_from_mesh + cvx_builder_lod produce (read them with cvx_builder_lod, release with cvx_builder_free). A triangle that
+ * covers more than 262144 voxels (VOXELIZE_BUFFER_MAX, WordBuilder.cs:37: the reference truncates it in scan order) is refused with
+ * CVX_ERR_INVALID_ARGUMENT — use the host builder for such meshes. */
+int cvx_gpu_builder_from_mesh(cvx_ctx* ctx, const float* positions, const uint8_t* colors32, int32_t n_vertices,
+                              int32_t max_dimension, const int32_t flips[3], int32_t n_lods, cvx_world_builder** out);
 /* Parse a text .obj (v with optional rgb, f with v, v/vt, v/vt/vn or v//vn) into the arrays above. */
 int cvx_obj_parse(const char* path, int32_t swap_yz, float** out_positions, uint8_t** out_colors32,
                   int32_t* out_n_vertices);

@@ -300,6 +300,43 @@ def test_debug_views_and_presentation(cv, orc, rm, mill_world, tmp_path):
         rm.blit_raybuffer(2)
 
 
+def test_gpu_world_builder_matches_host_builder(cv, rm):
+    """f2: voxelizer + RLE + LOD mips on the device (cvx_gpu_builder_from_mesh) against the host restatement of
+    VoxelizerHelper / WorldBuilder.ToFinalColumn / World.DownSample — every LOD blob byte for byte, voxel counts included."""
+    import time
+    for maxdim in (128, 256, 1024):
+        t0 = time.perf_counter()
+        host = cv.World.from_obj(MILL, maxdim)
+        t1 = time.perf_counter()
+        dev = rm.build_world_from_obj(MILL, maxdim)
+        t2 = time.perf_counter()
+        assert dev.dims == host.dims and dev.column_counts == host.column_counts and dev.voxel_counts == host.voxel_counts
+        for lod, (a, b) in enumerate(zip(dev.blobs, host.blobs)):
+            assert a.nbytes == b.nbytes, f"mill {maxdim} LOD {lod}: blob sizes {a.nbytes} != {b.nbytes}"
+            assert np.array_equal(a, b), f"mill {maxdim} LOD {lod}: {int((a != b).sum())} bytes differ"
+        print(f"mill {maxdim}^3: host builder {t1 - t0:.3f} s, device builder {t2 - t1:.3f} s (incl. blob download), {host.voxel_counts[0]} voxels")
+    # a random triangle soup with random vertex colours, non-cubic dimensions, all three flips
+    rng = np.random.default_rng(17)
+    pos = rng.uniform(0.0, 1.0, size=(300 * 3, 3)).astype(np.float32) * np.array([1.0, 0.45, 0.7], dtype=np.float32)
+    tri_c = rng.uniform(0.0, 1.0, size=(300, 1, 3)).astype(np.float32)
+    pos = (tri_c + 0.08 * (pos.reshape(300, 3, 3) - 0.5)).reshape(-1, 3).astype(np.float32)
+    col = rng.integers(0, 256, size=(900, 4), dtype=np.uint8)
+    col[:, 3] = 255
+    for flips in ((False, False, False), (True, True, True)):
+        host = cv.World.from_mesh(pos, col, 200, flips=flips)
+        dev = rm.build_world_from_mesh(pos, col, 200, flips=flips)
+        assert dev.dims == host.dims and dev.voxel_counts == host.voxel_counts
+        for lod, (a, b) in enumerate(zip(dev.blobs, host.blobs)):
+            assert np.array_equal(a, b), f"soup flips {flips} LOD {lod}"
+    # fewer LODs on request
+    dev3 = rm.build_world_from_mesh(pos, col, 200, flips=flips, lods=3)
+    assert len(dev3.blobs) == 3
+    for a, b in zip(dev3.blobs, host.blobs[:3]):
+        assert np.array_equal(a, b)
+    with pytest.raises(cv.CvxError):
+        rm.build_world_from_mesh(pos[:2], col[:2], 200)
+
+
 def test_error_paths(cv):
     from cpuvox_b200 import native as N
     m = cv.RenderManager(0)
