@@ -408,3 +408,34 @@ def test_large_terrain_world_config2(cv, orc, rm):
     pose = cv.CameraPose.from_euler((512.0, 700.0, 512.0), (3.0, 30.0, 0.0), far_clip=2048.0)
     s = rm.make_setup(pose)
     _assert_same(_gpu_frame(rm, s, 0), _oracle_frame(orc, ow, s, W, H, 0), "terrain1024 4K pitch 3")
+
+
+def test_structure_world_8k_and_batched_cameras_configs_4_5(cv, orc, rm):
+    """BASELINE config 4 shape (boxes/pipes/slabs world with many multi-run columns, 7680x4320, far 4x the world) and config 5
+    shape (seeded random cameras at 1280x720 over the terrain, rendered as one batch) at test size; the full-size runs are
+    tools/configs_check.py (results in DESIGN.md §7)."""
+    world = cv.World.synthetic(1, (1024, 256, 1024), seed=7)
+    ow = orc.OracleWorld(world.dims, world.blobs, world.column_counts)
+    rm.upload_world(world)
+    W, H = 7680, 4320
+    rm.set_resolution(W, H)
+    for pos, euler in (((512.5, 180.5, 512.5), (35.0, 20.0, 0.0)), ((100.5, 90.5, 200.5), (8.0, 50.0, 0.0))):
+        s = rm.make_setup(cv.CameraPose.from_euler(pos, euler, far_clip=2048.0))
+        _assert_same(_gpu_frame(rm, s, 0), _oracle_frame(orc, ow, s, W, H, 0), f"structures 8K {pos}")
+    terrain = cv.World.synthetic(0, (1024, 1024, 1024), seed=1234)
+    ow = orc.OracleWorld(terrain.dims, terrain.blobs, terrain.column_counts)
+    rm.upload_world(terrain)
+    W, H = 1280, 720
+    rm.set_resolution(W, H)
+    rng = np.random.default_rng(99)
+    poses = [cv.CameraPose.from_euler((float(rng.uniform(0, 1024)), float(rng.uniform(800, 950)), float(rng.uniform(0, 1024))),
+                                      (float(rng.uniform(-30, 80)), float(rng.uniform(0, 360)), 0.0), far_clip=2048.0) for _ in range(12)]
+    setups = [rm.make_setup(p) for p in poses]
+    dst = cv.alloc_pinned((len(setups), H, W))
+    rm.set_counters(False)
+    rm.draw_batch(setups, dst)
+    rm.set_counters(True)
+    for i, s in enumerate(setups):
+        o = _oracle_frame(orc, ow, s, W, H, 0)
+        assert np.array_equal(dst[i], o[3]), f"batched camera {i}"
+    cv.native.lib.cvx_free_pinned(dst.ctypes.data)
