@@ -17,7 +17,6 @@
 #include "../../include/cpuvox_b200.h"
 #include "device_types.h"
 #include "host_frame.h"
-#include "world_transcode.h"
 #include "world_builder.h"
 
 static_assert(sizeof(cvx_ray_state) == sizeof(cvxd_ray_state), "ray state layout");
@@ -190,6 +189,38 @@ void free_world(cvx_ctx* ctx) {
     memset(&ctx->world, 0, sizeof ctx->world);
 }
 
+// Takes ownership of `dblob` (a whole LOD blob in device memory: column_count 12-byte headers + element area), builds the Phase-1
+// tables from it on the device (world_builder_gpu.cu: the same tables world_transcode.h builds on the host for the emulator; it
+// also validates what the kernels index with) and makes it LOD `lod` of the context's world.
+int install_lod(cvx_ctx* ctx, int lod, int dim_x, int dim_y, int dim_z, void* dblob, int64_t bytes, int column_count) {
+    const int64_t needCols = (int64_t)(dim_x >> lod) * (dim_z >> lod);
+    const int64_t headerBytes = 12 * (int64_t)column_count;
+    const int64_t elementCells = (bytes - headerBytes) / 4;
+    void* headers = nullptr; void* bounds = nullptr; int regular = 0; long long bad = -1;
+    std::string err;
+    int r = cvxd_transcode_lod_device(ctx->stream, dblob, needCols, column_count, elementCells, lod, dim_y, &headers, &bounds, &regular, &bad, &ctx->launches, err);
+    if (r) {
+        cudaFree(dblob);
+        if (r == CVX_ERR_FORMAT) return fail(ctx, CVX_ERR_FORMAT, "column %lld of LOD %d points outside the element area", bad, lod);
+        return fail(ctx, r, "world upload failed: %s", err.c_str());
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->lodHeaders[lod]); cudaFree(ctx->lodElements[lod]); cudaFree(ctx->lodBounds[lod]);
+    ctx->lodHeaders[lod] = headers; ctx->lodElements[lod] = dblob; ctx->lodBounds[lod] = bounds;
+    ctx->world.dim_x = dim_x; ctx->world.dim_y = dim_y; ctx->world.dim_z = dim_z;
+    cvxd_lod& l = ctx->world.lods[lod];
+    l.headers = (const uint4*)headers;
+    l.elements = (const uint32_t*)((const uint8_t*)dblob + headerBytes); // the reference element area, verbatim
+    l.bounds = (const uint2*)bounds;
+    l.mul_x = dim_z >> lod;
+    l.lod = lod;
+    ctx->lodRegular[lod] = regular != 0;
+    ctx->world.regular = 1;
+    for (int i = 0; i < CVX_LOD_LEVELS; i++) if (ctx->lodHeaders[i] && !ctx->lodRegular[i]) ctx->world.regular = 0;
+    if (lod + 1 > ctx->world.lod_count) ctx->world.lod_count = lod + 1;
+    return CVX_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -281,41 +312,13 @@ int cvx_world_upload(cvx_ctx* ctx, int32_t lod, int32_t dim_x, int32_t dim_y, in
     if (bytes < headerBytes || ((bytes - headerBytes) & 3)) return fail(ctx, CVX_ERR_FORMAT, "blob of %lld bytes cannot hold %d column headers", (long long)bytes, column_count);
     if (ctx->world.lod_count > 0 && (ctx->world.dim_x != dim_x || ctx->world.dim_y != dim_y || ctx->world.dim_z != dim_z))
         return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "LOD %d dimensions differ from the already uploaded world; call cvx_world_free first", lod);
-    const int64_t elementCells = (bytes - headerBytes) / 4;
-    // transcode on the host (world_transcode.h); it also validates what the kernels index with: offsets + run counts must
-    // stay inside the element area
-    cvxh_lod_tables tables;
-    if (!cvxh_transcode_lod(blob, needCols, column_count, elementCells, lod, dim_y, tables))
-        return fail(ctx, CVX_ERR_FORMAT, "column %lld of LOD %d points outside the element area", (long long)tables.bad_column, lod);
+    // the raw blob goes to the device as it is (host or device source: unified addressing) and is transcoded there
     CU(ctx, cudaSetDevice(ctx->device));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->lodHeaders[lod]); cudaFree(ctx->lodElements[lod]); cudaFree(ctx->lodBounds[lod]);
-    ctx->lodHeaders[lod] = ctx->lodElements[lod] = ctx->lodBounds[lod] = nullptr;
-    const size_t boundBytes = tables.bounds.size() * sizeof(cvxh_u2);
-    cudaError_t e = cudaMalloc(&ctx->lodHeaders[lod], (size_t)(16 * needCols));
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->lodElements[lod], (size_t)(elementCells > 0 ? 4 * elementCells : 4));
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->lodBounds[lod], boundBytes ? boundBytes : 8);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->lodHeaders[lod], tables.headers.data(), (size_t)(16 * needCols), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess && elementCells > 0) e = cudaMemcpyAsync(ctx->lodElements[lod], (const uint8_t*)blob + headerBytes, (size_t)(4 * elementCells), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess && boundBytes) e = cudaMemcpyAsync(ctx->lodBounds[lod], tables.bounds.data(), boundBytes, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) {
-        cudaFree(ctx->lodHeaders[lod]); cudaFree(ctx->lodElements[lod]); cudaFree(ctx->lodBounds[lod]);
-        ctx->lodHeaders[lod] = ctx->lodElements[lod] = ctx->lodBounds[lod] = nullptr;
-        return fail(ctx, e == cudaErrorMemoryAllocation ? CVX_ERR_OUT_OF_MEMORY : CVX_ERR_CUDA, "world upload failed: %s", cudaGetErrorString(e));
-    }
-    ctx->world.dim_x = dim_x; ctx->world.dim_y = dim_y; ctx->world.dim_z = dim_z;
-    cvxd_lod& l = ctx->world.lods[lod];
-    l.headers = (const uint4*)ctx->lodHeaders[lod];
-    l.elements = (const uint32_t*)ctx->lodElements[lod];
-    l.bounds = (const uint2*)ctx->lodBounds[lod];
-    l.mul_x = dim_z >> lod;
-    l.lod = lod;
-    ctx->lodRegular[lod] = tables.regular;
-    ctx->world.regular = 1;
-    for (int i = 0; i < CVX_LOD_LEVELS; i++) if (ctx->lodHeaders[i] && !ctx->lodRegular[i]) ctx->world.regular = 0;
-    if (lod + 1 > ctx->world.lod_count) ctx->world.lod_count = lod + 1;
-    return CVX_OK;
+    void* dblob = nullptr;
+    cudaError_t e = cudaMalloc(&dblob, (size_t)(bytes > 0 ? bytes : 4));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dblob, blob, (size_t)bytes, cudaMemcpyDefault, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(dblob); return fail(ctx, e == cudaErrorMemoryAllocation ? CVX_ERR_OUT_OF_MEMORY : CVX_ERR_CUDA, "world upload failed: %s", cudaGetErrorString(e)); }
+    return install_lod(ctx, lod, dim_x, dim_y, dim_z, dblob, bytes, column_count);
 }
 
 int cvx_world_free(cvx_ctx* ctx) {
@@ -534,9 +537,39 @@ int cvx_gpu_builder_from_mesh(cvx_ctx* ctx, const float* positions, const uint8_
     b->dims[0] = dims[0]; b->dims[1] = dims[1]; b->dims[2] = dims[2];
     b->deviceBuilt = true;
     std::string err;
-    r = cvxd_build_world_gpu(ctx->device, ctx->stream, xyz.data(), colors32, n_vertices, n_lods, b, &ctx->launches, err);
+    r = cvxd_build_world_gpu(ctx->device, ctx->stream, xyz.data(), colors32, n_vertices, n_lods, b, nullptr, &ctx->launches, err);
     if (r) { cvx_builder_free(b); return fail(ctx, r, "device world build failed: %s", err.c_str()); }
     *out = b;
+    return CVX_OK;
+}
+
+// Mesh -> resident world without leaving the device: the LOD blobs produced by the device builder are transcoded in place and become
+// the context's world (as if cvx_world_free + cvx_world_upload had been called with them). Nothing is copied to the host.
+int cvx_world_build_from_mesh(cvx_ctx* ctx, const float* positions, const uint8_t* colors32, int32_t n_vertices, int32_t max_dimension,
+                              const int32_t flips[3], int32_t n_lods, int32_t out_dims[3], int64_t out_voxel_counts[CVX_LOD_LEVELS]) {
+    if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
+    if (!positions || !colors32 || n_vertices < 3 || max_dimension < 1 || n_lods < 1 || n_lods > CVX_LOD_LEVELS)
+        return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "bad mesh arguments");
+    std::vector<float> xyz;
+    int dims[3];
+    int r = cvxh_remap_mesh(positions, n_vertices, max_dimension, flips, xyz, dims);
+    if (r) return fail(ctx, r, "mesh cannot be remapped to max dimension %d", max_dimension);
+    auto pow2 = [](int n) { return n > 0 && (n & (n - 1)) == 0; };
+    if (!pow2(dims[0]) || !pow2(dims[2])) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "world dimensions %dx%dx%d: x/z must be powers of two", dims[0], dims[1], dims[2]);
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    free_world(ctx);
+    cvx_world_builder b;
+    b.dims[0] = dims[0]; b.dims[1] = dims[1]; b.dims[2] = dims[2];
+    b.deviceBuilt = true;
+    cvxd_lod_sink sink = [&](int lod, void* dblob, int64_t bytes, int columnCount) {
+        return install_lod(ctx, lod, dims[0], dims[1], dims[2], dblob, bytes, columnCount);
+    };
+    std::string err;
+    r = cvxd_build_world_gpu(ctx->device, ctx->stream, xyz.data(), colors32, n_vertices, n_lods, &b, &sink, &ctx->launches, err);
+    if (r) { free_world(ctx); return ctx->error.empty() || r != CVX_ERR_FORMAT ? fail(ctx, r, "device world build failed: %s", err.c_str()) : r; }
+    if (out_dims) { out_dims[0] = dims[0]; out_dims[1] = dims[1]; out_dims[2] = dims[2]; }
+    if (out_voxel_counts) for (int i = 0; i < CVX_LOD_LEVELS; i++) out_voxel_counts[i] = i < n_lods ? b.lods[i].voxelCount : 0;
     return CVX_OK;
 }
 

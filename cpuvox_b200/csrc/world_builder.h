@@ -41,8 +41,15 @@ int cvxh_remap_mesh(const float* positions, int32_t n_vertices, int32_t max_dime
                     std::vector<float>& out_xyz, int out_dims[3]);
 
 #ifdef __CUDACC__
+#include <functional>
 #include <string>
-/* world_builder_gpu.cu: voxelize + RLE + LOD mips on the device into b->lods[0 .. n_lods) (b->dims set by the caller). */
+/* Receives each finished LOD blob while it is still in device memory and takes ownership of the allocation (cudaFree it). */
+typedef std::function<int(int lod, void* device_blob, int64_t bytes, int column_count)> cvxd_lod_sink;
+/* world_builder_gpu.cu: voxelize + RLE + LOD mips on the device (b->dims set by the caller). Without a sink the blobs are copied into
+ * b->lods[0 .. n_lods); with one they are handed over on the device and b only records column and voxel counts. */
 int cvxd_build_world_gpu(int device, cudaStream_t stream, const float* xyz, const uint8_t* colors32, int32_t n_vertices, int32_t n_lods,
-                         cvx_world_builder* b, int64_t* launches, std::string& err);
+                         cvx_world_builder* b, const cvxd_lod_sink* sink, int64_t* launches, std::string& err);
+/* world_builder_gpu.cu: the Phase-1 tables of one LOD (uint4 headers + boundary records, see world_transcode.h) from a blob in device memory. */
+int cvxd_transcode_lod_device(cudaStream_t stream, const void* blob_dev, int64_t need_cols, int64_t column_count, int64_t element_cells, int lod, int dim_y,
+                              void** out_headers, void** out_bounds, int* out_regular, long long* bad_column, int64_t* launches, std::string& err);
 #endif

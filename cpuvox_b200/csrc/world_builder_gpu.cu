@@ -22,7 +22,9 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <climits>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -266,7 +268,7 @@ int sort_and_merge(DeviceBuffers& mem, unsigned long long* keys, uint32_t* vals,
 
 // sorted unique voxels of one LOD -> blob in the reference layout, copied into `blob`
 int encode_lod(DeviceBuffers& mem, const unsigned long long* ukeys, const uint32_t* ucolors, int64_t nVox, int dimX, int dimY, int dimZ, int lod,
-               cudaStream_t stream, cvx_lod_blob& blob, std::string& err) {
+               cudaStream_t stream, cvx_lod_blob& blob, const cvxd_lod_sink* sink, std::string& err) {
     const int64_t nCols = (int64_t)(dimX >> lod) * (dimZ >> lod);
     const int columnCount = (int)(((int64_t)dimX * dimZ) / ((int64_t)(lod + 1) * (lod + 1))); // World.ColumnCount (World.cs:17)
     unsigned long long *sizes, *offsets;
@@ -292,20 +294,123 @@ int encode_lod(DeviceBuffers& mem, const unsigned long long* ukeys, const uint32
     rle_kernel<false><<<blocks, 128, 0, stream>>>(ukeys, ucolors, nVox, nCols, topY, voxelScale, nullptr, offsets,
                                                     (uint32_t*)dblob, (uint32_t*)(dblob + 12 * (int64_t)columnCount));
     CK(cudaGetLastError());
+    blob.columnCount = columnCount; blob.voxelCount = nVox;
+    mem.release(tmp); mem.release(sizes); mem.release(offsets);
+    if (sink && *sink) {
+        // hand the device blob over (the sink takes ownership: the world stays resident, nothing goes through the host)
+        CK(cudaStreamSynchronize(stream));
+        for (auto& q : mem.all) if (q == dblob) q = nullptr;
+        int r = (*sink)(lod, dblob, (int64_t)bytes, columnCount);
+        if (r) { err = "installing the device-built LOD failed"; return r; }
+        return CVX_OK;
+    }
     blob.bytes.resize(bytes);
     CK(cudaMemcpyAsync(blob.bytes.data(), dblob, bytes, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
-    blob.columnCount = columnCount; blob.voxelCount = nVox; blob.built = true;
-    mem.release(dblob); mem.release(tmp); mem.release(sizes); mem.release(offsets);
+    blob.built = true;
+    mem.release(dblob);
     return CVX_OK;
 }
+
+// ---- device-side transcode of one LOD blob into the Phase-1 layout (same tables as world_transcode.h builds on the host) -----------
+// blob words: 3 per column header {elementOffset, runCount | worldMin << 16, worldMax | pad << 16}, then the element area.
+__global__ void transcode_count_kernel(const uint32_t* __restrict__ words, int64_t needCols, int64_t elementCells,
+                                       unsigned long long* __restrict__ counts, long long* __restrict__ bad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= needCols) return;
+    const uint32_t w0 = words[3 * i], rc = words[3 * i + 1] & 0xffffu;
+    unsigned long long n = 0ull;
+    if (rc) {
+        const int32_t off = (int32_t)w0;
+        if (off < 0 || (int64_t)off + rc + 2 > elementCells) atomicMin(bad, (long long)i); // offsets + run counts must stay inside the element area
+        else n = rc + 1ull;
+    }
+    counts[i] = n;
+}
+
+__global__ void transcode_write_kernel(const uint32_t* __restrict__ words, const uint32_t* __restrict__ elements, int64_t needCols, int lod, int dimY,
+                                       const unsigned long long* __restrict__ offsets, uint4* __restrict__ headers, uint2* __restrict__ bounds,
+                                       int* __restrict__ irregular) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= needCols) return;
+    const uint32_t w0 = words[3 * i], w1 = words[3 * i + 1], w2 = words[3 * i + 2];
+    const uint32_t rc = w1 & 0xffffu;
+    uint4 h = make_uint4(w0, w1, w2 & 0xffffu, 0u);
+    if (rc) {
+        const unsigned long long o = offsets[i];
+        h.w = (uint32_t)o;
+        const int scale = 1 << lod;
+        long long y = dimY;
+        bool ok = true;
+        for (uint32_t k = 0; k < rc; k++) {
+            const uint32_t el = elements[(int64_t)(int32_t)w0 + 1 + k];
+            const int len = (int)(short)(el >> 16);
+            bounds[o + k] = make_uint2((uint32_t)(y < 0 ? 0 : y), el);
+            if (len <= 0) ok = false;
+            y -= (long long)len * scale;
+            if (y < 0) ok = false;
+        }
+        bounds[o + rc] = make_uint2((uint32_t)(y < 0 ? 0 : y), 0u);
+        if (y != 0) ok = false;
+        if (!ok) *irregular = 1;
+    }
+    headers[i] = h;
+}
+
+} // namespace
+
+// blob_dev: the whole LOD blob in device memory. Allocates *out_headers (needCols uint4) and *out_bounds; the element area stays
+// where it is (blob_dev + 12 * column_count). Returns CVX_ERR_FORMAT with *bad_column set when a column points outside the blob.
+int cvxd_transcode_lod_device(cudaStream_t stream, const void* blob_dev, int64_t need_cols, int64_t column_count, int64_t element_cells, int lod, int dim_y,
+                              void** out_headers, void** out_bounds, int* out_regular, long long* bad_column, int64_t* launches, std::string& err) {
+    *out_headers = nullptr; *out_bounds = nullptr; *out_regular = 0; *bad_column = -1;
+    DeviceBuffers mem;
+    const uint32_t* words = (const uint32_t*)blob_dev;
+    const uint32_t* elements = words + 3 * column_count;
+    unsigned long long *counts, *offsets; long long* bad; int* irregular;
+    CK(mem.alloc(&counts, (size_t)need_cols + 1)); CK(mem.alloc(&offsets, (size_t)need_cols + 1));
+    CK(mem.alloc(&bad, 1)); CK(mem.alloc(&irregular, 1));
+    const long long none = LLONG_MAX;
+    CK(cudaMemcpyAsync(bad, &none, 8, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemsetAsync(irregular, 0, 4, stream));
+    CK(cudaMemsetAsync(counts + need_cols, 0, 8, stream));
+    const unsigned blocks = (unsigned)((need_cols + 255) / 256);
+    transcode_count_kernel<<<blocks, 256, 0, stream>>>(words, need_cols, element_cells, counts, bad);
+    CK(cudaGetLastError());
+    size_t tmpBytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, counts, offsets, (int)(need_cols + 1), stream));
+    uint8_t* tmp; CK(mem.alloc(&tmp, tmpBytes));
+    CK(cub::DeviceScan::ExclusiveSum(tmp, tmpBytes, counts, offsets, (int)(need_cols + 1), stream));
+    long long hostBad = none; unsigned long long total = 0;
+    CK(cudaMemcpyAsync(&hostBad, bad, 8, cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(&total, offsets + need_cols, 8, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (hostBad != none) { *bad_column = hostBad; err = "column points outside the element area"; return CVX_ERR_FORMAT; }
+    void* headers = nullptr; void* bounds = nullptr;
+    CK(cudaMalloc(&headers, (size_t)(16 * need_cols)));
+    cudaError_t e = cudaMalloc(&bounds, total ? (size_t)total * 8 : 8);
+    if (e != cudaSuccess) { cudaFree(headers); err = cudaGetErrorString(e); return e == cudaErrorMemoryAllocation ? CVX_ERR_OUT_OF_MEMORY : CVX_ERR_CUDA; }
+    transcode_write_kernel<<<blocks, 256, 0, stream>>>(words, elements, need_cols, lod, dim_y, offsets, (uint4*)headers, (uint2*)bounds, irregular);
+    int hostIrregular = 1;
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&hostIrregular, irregular, 4, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { cudaFree(headers); cudaFree(bounds); err = cudaGetErrorString(e); return CVX_ERR_CUDA; }
+    if (launches) *launches += 2;
+    *out_headers = headers; *out_bounds = bounds;
+    // `bounds` offsets are 32-bit in the header and y is 16-bit in the kernels' records (world_transcode.h)
+    *out_regular = (!hostIrregular && dim_y <= 65535 && total < 0xffffffffull) ? 1 : 0;
+    return CVX_OK;
+}
+
+namespace {
 
 } // namespace
 
 // xyz: n_vertices x {x,y,z} already remapped (cvxh_remap_mesh); colors32: n_vertices x {r,g,b,a}. Fills b->lods[0 .. n_lods).
 // kernel_ms (optional): device time of the whole build. launches: kernels launched (ours + CUB's are not counted separately).
 int cvxd_build_world_gpu(int device, cudaStream_t stream, const float* xyz, const uint8_t* colors32, int32_t n_vertices, int32_t n_lods,
-                         cvx_world_builder* b, int64_t* launches, std::string& err) {
+                         cvx_world_builder* b, const cvxd_lod_sink* sink, int64_t* launches, std::string& err) {
     const int X = b->dims[0], Y = b->dims[1], Z = b->dims[2];
     const int64_t nTris = n_vertices / 3;
     if (Y > 65536 || (int64_t)X * Z > ((int64_t)1 << 40)) { err = "dimensions exceed the 16 + 40 bit record key"; return CVX_ERR_INVALID_ARGUMENT; }
@@ -347,7 +452,7 @@ int cvxd_build_world_gpu(int device, cudaStream_t stream, const float* xyz, cons
     if (r) return r;
     mem.release(keys); mem.release(vals);
     if (launches) *launches += 2;
-    r = encode_lod(mem, ukeys0, ucolors0, n0, X, Y, Z, 0, stream, b->lods[0], err);
+    r = encode_lod(mem, ukeys0, ucolors0, n0, X, Y, Z, 0, stream, b->lods[0], sink, err);
     if (r) return r;
     if (launches) *launches += 2;
     for (int lod = 1; lod < n_lods; lod++) {
@@ -362,7 +467,7 @@ int cvxd_build_world_gpu(int device, cudaStream_t stream, const float* xyz, cons
         unsigned long long* uk; uint32_t* uc; int64_t nj = 0;
         r = sort_and_merge(mem, kj, vj, n0, 16 + bits_for((unsigned long long)((int64_t)(X >> lod) * (Z >> lod))), stream, &uk, &uc, nj, err);
         if (r) return r;
-        r = encode_lod(mem, uk, uc, nj, X, Y, Z, lod, stream, b->lods[lod], err);
+        r = encode_lod(mem, uk, uc, nj, X, Y, Z, lod, stream, b->lods[lod], sink, err);
         if (r) return r;
         mem.release(kj); mem.release(vj); mem.release(uk); mem.release(uc);
         if (launches) *launches += 5;

@@ -1,7 +1,8 @@
 /*
  * world_transcode.h — host-side transcoding of one World LOD blob (the reference's allocator blob: ColumnCount 12-byte
  * RLEColumn headers, then the element area; Assets/Code/World.cs:161-209,285-313) into the device layout.
- * Header-only: shared by cvx_world_upload (capi.cu) and the test-only SIMT emulator (tools/simt_emu).
+ * Header-only. The product builds the same tables on the device (transcode_*_kernel in world_builder_gpu.cu, used by cvx_world_upload
+ * and cvx_world_build_from_mesh); this host version feeds the test-only SIMT emulator (tools/simt_emu) and documents the layout.
  *
  *   headers  one uint4 per addressed column (index (x >> lod) * (dimZ >> lod) + (z >> lod), World.cs:145-149):
  *              x = element offset (4-byte cells into the element area; colours at x + runCount + 2)

@@ -222,6 +222,20 @@ class RenderManager:
         self._ck(lib.cvx_gpu_builder_from_mesh(self._ctx, _ptr(positions), _ptr(colors32), positions.shape[0], max_dimension, C.byref(fl), lods, C.byref(b)))
         return World._from_builder(b, lods)
 
+    def build_resident_world_from_mesh(self, positions: np.ndarray, colors32: np.ndarray, max_dimension: int,
+                                       flips: Sequence[bool] = (False, False, False), lods: int = LOD_LEVELS) -> World:
+        """cvx_world_build_from_mesh: mesh -> LOD blobs -> Phase-1 tables without leaving the device; the result becomes this
+        context's world. Returns a World that carries only dimensions and voxel counts (the blobs exist on the GPU only)."""
+        positions = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        colors32 = np.ascontiguousarray(colors32, dtype=np.uint8).reshape(-1, 4)
+        fl = (C.c_int32 * 3)(*[int(bool(f)) for f in flips])
+        dims, vox = (C.c_int32 * 3)(), (C.c_int64 * LOD_LEVELS)()
+        self._ck(lib.cvx_world_build_from_mesh(self._ctx, _ptr(positions), _ptr(colors32), positions.shape[0], max_dimension, C.byref(fl), lods,
+                                               C.byref(dims), C.byref(vox)))
+        self.world = World((dims[0], dims[1], dims[2]), [], [], [int(v) for v in vox][:lods])
+        self._refresh_lods()
+        return self.world
+
     def build_world_from_obj(self, path: str, max_dimension: int = 1024, flips: Sequence[bool] = (True, False, False),
                              swap_yz: bool = False, lods: int = LOD_LEVELS) -> World:
         """ObjModel.Import on the host, then the conversion pipeline of UnityManager.cs:297-331 on the GPU."""

@@ -151,6 +151,7 @@ SYMBOLS = {
     "cvx_host_benchmark_length": (_F, []),
     "cvx_builder_from_mesh": (C.c_int, [_P, _P, _I32, _I32, C.POINTER(_I32 * 3), _I32, C.POINTER(_P)]),
     "cvx_gpu_builder_from_mesh": (C.c_int, [_P, _P, _P, _I32, _I32, C.POINTER(_I32 * 3), _I32, C.POINTER(_P)]),
+    "cvx_world_build_from_mesh": (C.c_int, [_P, _P, _P, _I32, _I32, C.POINTER(_I32 * 3), _I32, C.POINTER(_I32 * 3), C.POINTER(_I64 * LOD_LEVELS)]),
     "cvx_obj_parse": (C.c_int, [C.c_char_p, _I32, C.POINTER(_P), C.POINTER(_P), C.POINTER(_I32)]),
     "cvx_host_free": (None, [_P]),
     "cvx_builder_synthetic": (C.c_int, [_I32, _I32, _I32, _I32, _U32, _I32, C.POINTER(_P)]),

@@ -97,8 +97,8 @@ int cvx_set_stream(cvx_ctx* ctx, void* cuda_stream);
 
 /* ---- world hand-off: World / WorldAllocator, Assets/Code/World.cs:8-43,261-313 ------------
  * blob = WorldAllocator.GetStartPointer()/GetByteLength(): column_count 12-byte RLEColumn
- * headers followed by 4-byte RLEElement / ColorARGB32 cells. The host keeps its blob; the
- * library copies it to the device (and builds its own device-side header layout). */
+ * headers followed by 4-byte RLEElement / ColorARGB32 cells. The caller keeps its blob (host or device memory); the
+ * library copies it to its own device allocation and builds its Phase-1 tables from it with a CUDA kernel. */
 int cvx_world_upload(cvx_ctx* ctx, int32_t lod, int32_t dim_x, int32_t dim_y, int32_t dim_z,
                      const void* blob, int64_t bytes, int32_t column_count);
 int cvx_world_free(cvx_ctx* ctx);
@@ -267,6 +267,12 @@ int cvx_builder_from_mesh(const float* positions, const uint8_t* colors32, int32
  * CVX_ERR_INVALID_ARGUMENT — use the host builder for such meshes. */
 int cvx_gpu_builder_from_mesh(cvx_ctx* ctx, const float* positions, const uint8_t* colors32, int32_t n_vertices,
                               int32_t max_dimension, const int32_t flips[3], int32_t n_lods, cvx_world_builder** out);
+/* Mesh -> resident world entirely on the device: builds the LODs like cvx_gpu_builder_from_mesh and installs them as the context's
+ * world (replacing any uploaded one) without copying the blobs to the host. out_dims / out_voxel_counts (optional) receive the world
+ * dimensions and the per-LOD voxel counts the reference logs (UnityManager.cs:326-331). */
+int cvx_world_build_from_mesh(cvx_ctx* ctx, const float* positions, const uint8_t* colors32, int32_t n_vertices,
+                              int32_t max_dimension, const int32_t flips[3], int32_t n_lods, int32_t out_dims[3],
+                              int64_t out_voxel_counts[CVX_LOD_LEVELS]);
 /* Parse a text .obj (v with optional rgb, f with v, v/vt, v/vt/vn or v//vn) into the arrays above. */
 int cvx_obj_parse(const char* path, int32_t swap_yz, float** out_positions, uint8_t** out_colors32,
                   int32_t* out_n_vertices);

@@ -328,6 +328,17 @@ def test_gpu_world_builder_matches_host_builder(cv, rm):
         assert dev.dims == host.dims and dev.voxel_counts == host.voxel_counts
         for lod, (a, b) in enumerate(zip(dev.blobs, host.blobs)):
             assert np.array_equal(a, b), f"soup flips {flips} LOD {lod}"
+    # mesh -> resident world without leaving the device (cvx_world_build_from_mesh): frames equal those of the uploaded host-built world
+    W, H = 640, 360
+    rm.set_resolution(W, H)
+    rm.upload_world(host)
+    pose = cv.CameraPose.from_euler((0.5 * host.dims[0], 0.9 * host.dims[1], 0.5 * host.dims[2]), (50.0, 20.0, 0.0), far_clip=2.0 * host.max_dimension)
+    want = _gpu_frame(rm, rm.make_setup(pose), 0)
+    res = rm.build_resident_world_from_mesh(pos, col, 200, flips=flips)
+    assert res.dims == host.dims and res.voxel_counts == host.voxel_counts and rm.world_is_regular()
+    got = _gpu_frame(rm, rm.make_setup(pose), 0)
+    _assert_same(got, want, "resident device-built world")
+    assert int((got[3] != SKY).sum()) > 1000
     # fewer LODs on request
     dev3 = rm.build_world_from_mesh(pos, col, 200, flips=flips, lods=3)
     assert len(dev3.blobs) == 3
