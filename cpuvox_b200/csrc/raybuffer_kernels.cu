@@ -33,9 +33,11 @@
 #define FULL_MASK 0xffffffffu
 #if defined(CVX_EMU) && defined(CVX_EMU_STATS) /* emulator-only event counts per ray (tools/simt_emu), lane 0 of the group counts */
 #define EMU_STAT(i) do { if (gl == 0) emu_stats[(int64_t)flat * 16 + (i)]++; } while (0)
+#define EMU_STAT_ADD(i, v) do { if (gl == 0) emu_stats[(int64_t)flat * 16 + (i)] += (unsigned long long)(v); } while (0)
 extern unsigned long long* emu_stats;
 #else
 #define EMU_STAT(i) do { } while (0)
+#define EMU_STAT_ADD(i, v) do { } while (0)
 #endif
 #define SKYBOX_ARGB 0x191919FFu /* ColorARGB32(25,25,25): bytes a=255,r,g,b (DrawSegmentRayJob.cs:702) */
 
@@ -126,35 +128,9 @@ __device__ bool dda_step_to_world(Dda& d, float dimX, float dimZ) { // StepToWor
 
 // ---- CameraData clip helpers (Assets/Code/Utils/CameraData.cs:50-157) --------------------------------------
 __device__ __forceinline__ float cross2(float ax, float ay, float bx, float by) { return ax * by - ay * bx; }
-__device__ __forceinline__ float clip_min(F3 pMin, F3 pMax, float frustum) { // :101-107
-    float fi = 1.0f / frustum;
-    float c0 = cross2(1.0f, fi, pMax.x, pMax.z);
-    float c1 = cross2(1.0f, fi, pMin.x, pMin.z);
-    return 1.0f - (c0 / (c0 - c1));
-}
-__device__ __forceinline__ float clip_max(F3 pMin, F3 pMax, float frustum) { // :109-115
-    float fi = 1.0f / frustum;
-    float c0 = cross2(1.0f, fi, pMax.x, pMax.z);
-    float c1 = cross2(1.0f, fi, pMin.x, pMin.z);
-    return c1 / (c1 - c0);
-}
-__device__ bool world_bounds_clipping(F3 pMin, F3 pMax, float bMin, float bMax, float& minLerp, float& maxLerp) { // :50-99
-    minLerp = 0.0f; maxLerp = 1.0f;
-    if (pMin.x > pMin.z * bMax) {
-        if (pMax.x > pMax.z * bMax) return true;
-        minLerp = clip_min(pMin, pMax, bMax);
-        if (pMax.x < pMax.z * bMin) maxLerp = clip_max(pMin, pMax, bMin);
-    } else if (pMax.x > pMax.z * bMax) {
-        maxLerp = clip_max(pMin, pMax, bMax);
-        if (pMin.x < pMin.z * bMin) minLerp = clip_min(pMin, pMax, bMin);
-    } else if (pMin.x < pMin.z * bMin) {
-        if (pMax.x < pMax.z * bMin) return true;
-        minLerp = clip_min(pMin, pMax, bMin);
-    } else if (pMax.x < pMax.z * bMin) {
-        maxLerp = clip_max(pMin, pMax, bMin);
-    }
-    return false;
-}
+// GetWorldBoundsClippingCamSpace (:50-99) is evaluated lane-parallel inside the frustum re-narrowing of phase1_kernel: four lanes, one
+// (line, end) pair each; ClipMin (:101-107) = 1 - c0 / (c0 - c1), ClipMax (:109-115) = c1 / (c1 - c0) with
+// c0 = cross((1, 1/frustum), pMax.xz), c1 = cross((1, 1/frustum), pMin.xz).
 __device__ __forceinline__ bool clip_near(F3& a, F3& b) { // :123-137, near plane z' <= 0 (F3.y)
     if (a.y <= 0.0f) {
         if (b.y <= 0.0f) return false;
@@ -345,8 +321,7 @@ __device__ __forceinline__ void touch(const uint32_t* p) {
 #ifdef CVX_EMU
     (void)p;
 #else
-    uint32_t sink;
-    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(sink) : "l"(p));
+    asm volatile("{ .reg .u32 sink; ld.global.nc.u32 sink, [%0]; }" :: "l"(p));
 #endif
 }
 
@@ -709,6 +684,9 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                         if (inRound) scratch[myBase] = gl;           // first lane of each cached column -> its batch cell
                         const uint32_t startMask = __reduce_or_sync(gmask, inRound ? (1u << myBase) : 0u);
                         const int totalRuns = GSHFL(incl, 31 - __clz(roundCols));
+                        EMU_STAT_ADD(9, totalRuns);            // lanes used by the rounds
+                        EMU_STAT_ADD(10, __popc(roundCols));   // columns cached by the rounds
+                        EMU_STAT_ADD(11, __popc(consider));    // columns that were candidates for the round
                         __syncwarp(gmask);
                         const int myStart = 31 - __clz(startMask & ((2u << gl) - 1u)); // lane 0 always starts a column
                         const bool hasRun = gl < totalRuns;
