@@ -116,6 +116,14 @@ def ncu_traffic(W):
     return None
 
 
+def ncu_instructions(W):
+    """Mean warp instructions per Phase-1 launch over the 60 poses, from the committed ncu pass (profiles/phase1_inst.json)."""
+    p = os.path.join(ROOT, "profiles", "phase1_inst.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(str(W))
+    return None
+
+
 def phase1_bytes(c):
     """Phase-1 share of the algorithmic bytes: headers, runs, colour gather, raybuffer writes."""
     return 12 * c["dda_steps"] + 4 * c["runs_visited"] + 4 * c["px_voxel"] + 4 * (c["px_voxel"] + c["px_sky"])
@@ -306,6 +314,15 @@ def run_b200(a, rank, local_rank, world_size):
     peak, peak_src = measured_hbm_peak()
     achieved = p1_bytes / (p1_ms * 1e-3) / 1e9 if p1_ms > 0 else 0.0
     frame_bytes = sum(cv.algorithmic_bytes(c, W, H) for c in per) / len(per)
+    # what actually bounds Phase 1: issue slots (148 SMs x 4 schedulers x SM clock); instruction counts come from the committed ncu pass
+    inst = ncu_instructions(W)
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    issue = None
+    if inst and p1_ms > 0:
+        slots_per_s = 148 * 4 * sm_mhz * 1e6
+        issue = {"warp_instructions_per_launch": inst, "source": "profiles/phase1_inst.json (ncu smsp__inst_executed.sum, mean over the 60 poses)",
+                 "issue_slot_utilisation": inst / (p1_ms * 1e-3) / slots_per_s,
+                 "note": "Phase 1 is latency/issue bound (DESIGN.md §7): this, not the HBM fraction, tracks kernel quality"}
 
     if rank != 0:
         if world_size > 1:
@@ -333,6 +350,7 @@ def run_b200(a, rank, local_rank, world_size):
             "peak_source": peak_src, "algorithmic_bytes_per_launch": p1_bytes, "traffic": ncu_traffic(W),
             "exclusive": {"launch_ms": x1_ms, "achieved": p1_bytes / (x1_ms * 1e-3) / 1e9 if x1_ms > 0 else 0.0,
                           "note": "same launches with one view in flight (each alone on the GPU), measured after the timed region"},
+            "issue": issue,
             "whole_frame": {"algorithmic_bytes": frame_bytes, "achieved": frame_bytes * fps / world_size / 1e9,
                             "frac": frame_bytes * fps / world_size / 1e9 / peak},
         },
