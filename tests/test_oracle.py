@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import POSES, ROOT, crc, pose_for, setup_for
+from conftest import MILL, POSES, ROOT, crc, pose_for, setup_for
 from rle import encode_world
 
 SKY = 0x191919FF
@@ -252,3 +252,37 @@ def test_oracle_matches_golden_fixtures(cv, orc, terrain_world, structure_world,
             frame = orc.blit(orc.copy_setup(s), W, H, td, lr)
             assert cn == c["counters"], (name, c["pose"], W, H)
             assert (crc(td), crc(lr), crc(frame)) == (c["td_crc"], c["lr_crc"], c["frame_crc"]), (name, c["pose"], W, H)
+
+
+def test_python_restatement_agrees(cv, orc):
+    """Two independent restatements of the reference's Phase 1 — oracle/cpuvox_oracle.cpp (C++) and oracle/pyref.py (pure Python,
+    written from the C# alone) — must produce identical raybuffers: a transcription slip in either shows up here. Covers LOD
+    switches (far clip 6x the world), rays starting outside the world, inverted run order, rolled cameras, multi-run columns,
+    tall columns and cameras inside geometry (near-plane clipping of runs)."""
+    from conftest import COMB_POSES, comb_world
+    from oracle import pyref
+
+    def check(world, W, H, poses, what, lods=None):
+        ow = orc.OracleWorld(world.dims, world.blobs, world.column_counts)
+        pw = [pyref.PyWorldLod(world.dims, lod, world.blobs[lod], world.column_counts[lod]) for lod in range(len(world.blobs))]
+        if lods is None:
+            lods = cv.setup_lods(world.max_dimension, W, H)
+        for i, pose in enumerate(poses):
+            s = cv.frame_setup(pose, W, H, lods, world.dims[1])
+            otd, olr, cn = orc.render_raybuffers(ow, orc.copy_setup(s), W, H)
+            ptd, plr = pyref.render_raybuffers(pw, s, W, H)
+            bad = int((otd != ptd).sum() + (olr != plr).sum())
+            assert bad == 0, f"{what} pose {i}: {bad} raybuffer pixels differ between the two restatements"
+            assert cn["px_voxel"] + cn["px_sky"] == int((ptd != 0).sum() + (plr != 0).sum())
+            os_ = orc.copy_setup(s)
+            assert np.array_equal(orc.blit(os_, W, H, otd, olr), pyref.blit(s, W, H, ptd, plr)), f"{what} pose {i}: Phase 2 differs"
+
+    terrain = cv.World.synthetic(0, (64, 64, 64), seed=3)
+    check(terrain, 96, 64, [pose_for(cv, terrain, POSES[k]) for k in (0, 2, 3, 5, 8)], "terrain")
+    structures = cv.World.synthetic(1, (128, 64, 64), seed=7)
+    check(structures, 120, 90, [pose_for(cv, structures, POSES[k]) for k in (1, 4, 7)], "structures")
+    mill = cv.World.from_obj(MILL, 128)
+    check(mill, 64, 48, [pose_for(cv, mill, POSES[k], far_scale=6.0) for k in (0, 2, 6)], "mill, far clip 6x (LOD switches)")
+    comb, _, _ = comb_world(cv)
+    check(comb, 80, 60, [cv.CameraPose.from_euler(p, e, far_clip=200.0) for p, e in COMB_POSES], "comb (tall columns, near plane)",
+          lods=np.full(6, 1e9, dtype=np.float32))   # a single-LOD world: no LOD switches
