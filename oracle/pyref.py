@@ -579,3 +579,98 @@ def blit(setup, W, H, td, lr):
             r = np.clip(r, off, off + rc - 1)
             frame[sel] = td[r, ys[sel]] if k < 2 else lr[r, xs[sel]]
     return frame
+
+
+# ---- host setup (logic cross-check in float64; the float32 restatements are the library's host_setup.cpp and the C++ oracle) ------
+def _quat_rotate(q, v):
+    x, y, z, w = q
+    u = np.array([x, y, z], dtype=np.float64)
+    v = np.asarray(v, dtype=np.float64)
+    return v + 2.0 * np.cross(u, np.cross(u, v) + w * v)
+
+
+def _signed_angle(a, b):                                           # Vector2.SignedAngle
+    den = np.sqrt(float(a[0] * a[0] + a[1] * a[1]) * float(b[0] * b[0] + b[1] * b[1]))
+    if den < 1e-15:
+        return 0.0
+    ang = np.degrees(np.arccos(np.clip((a[0] * b[0] + a[1] * b[1]) / den, -1.0, 1.0)))
+    return ang * (1.0 if a[0] * b[1] - a[1] * b[0] >= 0.0 else -1.0)
+
+
+def host_frame_setup(position, rotation, fov_y_degrees, near, far, W, H):
+    """RenderManager.DrawWorld up to DrawSegments (RenderManager.cs:119-152,374-501) + the CameraData ctor (CameraData.cs:18-36) in
+    float64. Returns dict(vp, segments=[(min_screen, max_screen, ray_min, ray_max, ray_count) or None], world_to_screen 4x4, inverse)."""
+    pos = np.asarray(position, dtype=np.float64)
+    fwd, up = _quat_rotate(rotation, (0, 0, 1)), _quat_rotate(rotation, (0, 1, 0))
+    t = np.tan(np.radians(fov_y_degrees) / 2.0)
+    aspect = W / H
+    proj = np.array([[1.0 / (aspect * t), 0, 0, 0], [0, 1.0 / t, 0, 0], [0, 0, -(far + near) / (far - near), -2.0 * far * near / (far - near)], [0, 0, -1, 0]])
+    right = np.cross(up, fwd)
+    right /= np.linalg.norm(right)                                 # Matrix4x4.LookAt(0, forward, up): columns right, up', forward (A4)
+    up2 = np.cross(fwd, right)
+    look = np.eye(4)
+    look[:3, 0], look[:3, 1], look[:3, 2] = right, up2, fwd / np.linalg.norm(fwd)
+    zflip = np.diag([1.0, 1.0, -1.0, 1.0])
+    # CalculateVanishingPointWorld :374-378: sin(eulerAngles.x) = -forward.y (A6)
+    vp_world = pos + np.array([0.0, 1.0, 0.0]) * (near / fwd[1])
+    local_to_screen = proj @ (zflip @ np.linalg.inv(look))         # :386-388
+    cam = local_to_screen @ np.append(vp_world - pos, 1.0)
+    vp = (cam[:2] / cam[3] * 0.5 + 0.5) * np.array([W, H], dtype=np.float64)
+    screen = np.array([W, H], dtype=np.float64)
+    to_local = look @ (np.linalg.inv(zflip) @ np.linalg.inv(proj))  # TransformPixel :487-500
+
+    def transform_pixel(px):
+        v = to_local @ np.array([(px[0] / W - 0.5) * 2.0, (px[1] / H - 0.5) * 2.0, 1.0, 1.0])
+        return np.array([v[0], v[2]]) / v[3]
+
+    def segment(dist, neutral, primary):                           # GetGenericSegmentParameters :402-501
+        sec = 1 - primary
+        smin = np.array([vp[sec] - dist] * 2)
+        smax = np.array([vp[sec] + dist] * 2)
+        a = vp[primary] + dist * np.sign(neutral[primary])
+        smin[primary] = smax[primary] = a
+        if smax[sec] <= 0.0 or smin[sec] >= screen[sec]:
+            return None
+        if (vp >= 0.0).all() and (vp <= screen).all():
+            mn, mx = smin, smax
+        else:
+            mid = (smin + 0.5 * (smax - smin)) - vp
+            ang_l, ang_r, dir_l, dir_r = 90.0, -90.0, np.zeros(2), np.zeros(2)
+            for corner in ((0.0, 0.0), (0.0, screen[1]), (screen[0], 0.0), (screen[0], screen[1])):
+                d = np.array(corner) - vp
+                scaled = d * (dist / abs(d[primary]))
+                ang = _signed_angle(neutral, d)
+                if ang < ang_l:
+                    ang_l, dir_l = ang, scaled
+                if ang > ang_r:
+                    ang_r, dir_r = ang, scaled
+            c_l, c_r = dir_l + vp, dir_r + vp
+            if ang_l < -45.0:
+                c_l = smin if _signed_angle(mid, smax) > 0.0 else smax      # (:466: a point passed as a direction, as in the reference)
+            if ang_r > 45.0:
+                c_r = smin if _signed_angle(mid, smax) < 0.0 else smax
+            swap = c_l[sec] > c_r[sec]
+            mn, mx = (c_r, c_l) if swap else (c_l, c_r)
+        count = max(0, int(np.rint(mx[sec] - mn[sec])))
+        return mn, mx, transform_pixel(mn), transform_pixel(mx), count
+
+    segs = [None] * 4
+    if vp[1] < H:
+        segs[0] = segment(H - vp[1], (0.0, 1.0), 1)
+    if vp[1] > 0.0:
+        segs[1] = segment(vp[1], (0.0, -1.0), 1)
+    if vp[0] < W:
+        segs[2] = segment(W - vp[0], (1.0, 0.0), 0)
+    if vp[0] > 0.0:
+        segs[3] = segment(vp[0], (-1.0, 0.0), 0)
+    # CameraData ctor: worldToCamera = Scale(1,1,-1) * inverse(TRS(pos, rot, 1)) (A3)
+    rot = np.eye(4)
+    rot[:3, 0], rot[:3, 1], rot[:3, 2] = _quat_rotate(rotation, (1, 0, 0)), up, fwd
+    trs = rot.copy()
+    trs[:3, 3] = pos
+    w2c = zflip @ np.linalg.inv(trs)
+    scale_half = np.diag([0.5, 0.5, 1.0, 1.0])
+    trans = np.eye(4)
+    trans[:3, 3] = (0.5, 0.5, 1.0)
+    w2s = np.diag([W, H, 1.0, 1.0]) @ (trans @ (scale_half @ (proj @ w2c)))
+    return {"vp": vp, "segments": segs, "world_to_screen": w2s, "inverse": bool(fwd[1] >= 0.0)}

@@ -286,3 +286,39 @@ def test_python_restatement_agrees(cv, orc):
     comb, _, _ = comb_world(cv)
     check(comb, 80, 60, [cv.CameraPose.from_euler(p, e, far_clip=200.0) for p, e in COMB_POSES], "comb (tall columns, near plane)",
           lods=np.full(6, 1e9, dtype=np.float32))   # a single-LOD world: no LOD switches
+
+
+def test_python_host_setup_agrees(cv):
+    """Logic cross-check of the host setup (vanishing point, GetGenericSegmentParameters with its clamped-segment branches, CameraData
+    matrix, RenderManager.cs:374-501, CameraData.cs:18-36): a float64 restatement written from the C# (oracle/pyref.py) against the
+    library's float32 one — same segments, same ray counts, same points up to float32 rounding."""
+    from oracle import pyref
+    lods = np.full(6, 1e9, dtype=np.float32)
+    cases = [((128.0, 200.0, 100.0), (60.0, 30.0, 0.0)), ((50.0, 90.0, 70.0), (85.0, -135.0, 0.0)), ((10.0, 20.0, 30.0), (-16.2, -135.0, 0.0)),
+             ((77.0, 60.0, 40.0), (3.0, 200.0, 0.0)), ((77.0, 60.0, 40.0), (-3.0, 20.0, 0.0)), ((30.0, 50.0, 90.0), (40.0, 10.0, 37.0)),
+             ((30.0, 50.0, 90.0), (59.12, -135.0, 180.0)), ((5.0, 9.0, 2.0), (20.0, 77.0, 90.0)), ((5.0, 9.0, 2.0), (-80.0, 0.0, 0.0)),
+             ((5.0, 9.0, 2.0), (12.0, 300.0, -60.0)), ((64.0, 64.0, 64.0), (30.0, 45.0, 10.0))]
+    for (W, H) in ((320, 180), (333, 217), (200, 400)):
+        for pos, euler in cases:
+            pose = cv.CameraPose.from_euler(pos, euler, far_clip=512.0)
+            s = cv.frame_setup(pose, W, H, lods, 256, limit_horizon=False)
+            r = pyref.host_frame_setup(pose.position, pose.rotation, pose.fov_y_degrees, pose.near_clip, pose.far_clip, W, H)
+            what = f"{W}x{H} pos {pos} euler {euler}"
+            vp = np.array(s.vanishing_point_screen[:], dtype=np.float64)
+            assert np.allclose(vp, r["vp"], rtol=2e-4, atol=2e-2), f"{what}: vanishing point {vp} vs {r['vp']}"
+            assert bool(s.camera.inverse_element_iteration_direction) == r["inverse"], what
+            m = np.array(s.camera.world_to_screen[:], dtype=np.float64).reshape(4, 4).T   # stored column after column
+            assert np.allclose(m, r["world_to_screen"], rtol=1e-4, atol=1e-2), f"{what}: world-to-screen matrix"
+            for k in range(4):
+                sg, want = s.segments[k], r["segments"][k]
+                if want is None:
+                    assert sg.ray_count == 0, f"{what} segment {k}: library has {sg.ray_count} rays, restatement none"
+                    continue
+                mn, mx, rmin, rmax, count = want
+                scale = max(1.0, float(np.abs(r["vp"]).max()))
+                assert abs(sg.ray_count - count) <= (1 if scale > 2000 else 0), f"{what} segment {k}: ray count {sg.ray_count} vs {count}"
+                tol = 2e-2 + 3e-5 * scale
+                assert np.allclose(sg.min_screen[:], mn, atol=tol) and np.allclose(sg.max_screen[:], mx, atol=tol), \
+                    f"{what} segment {k}: screen corners {sg.min_screen[:]} {sg.max_screen[:]} vs {mn} {mx}"
+                for got, ref in ((np.array(sg.cam_local_plane_ray_min[:]), rmin), (np.array(sg.cam_local_plane_ray_max[:]), rmax)):
+                    assert np.allclose(got, ref, rtol=2e-3, atol=1e-3 * max(1.0, float(np.abs(ref).max()))), f"{what} segment {k}: plane ray {got} vs {ref}"
