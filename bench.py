@@ -12,9 +12,9 @@ the reference's shipped dataset.
 value    frames/s with everything resident in HBM: per frame one Phase-1 and one Phase-2 launch; a step is one
          cvx_draw_batch over the 60 poses (device only), which keeps up to `frames_in_flight` views in flight, each on its own
          stream with its own raybuffers and framebuffer (the reference double-buffers its raybuffers for the same overlap).
-e2e      frames/s through the public C ABI with HOST buffers: per frame the host computes the segment/VP setup
-         (cvx_host_frame_setup), passes it by value (kernel parameters are the only host->device bytes) and receives the
-         finished frame in pinned host memory (cvx_draw_batch, copy overlapped with the next frame's kernels).
+e2e      frames/s through the public C ABI with HOST buffers (cvx_draw_world_batch = RenderManager.DrawWorld per camera): per
+         frame the host computes the segment/VP setup from the camera pose, passes it by value (kernel parameters are the only
+         host->device bytes) and receives the finished frame in pinned host memory (copy overlapped with the next frames' kernels).
 roofline Phase-1 kernel (dominant): algorithmic bytes of SURVEY.md §8(d) per launch / launch duration against the measured
          HBM copy bandwidth of MEASURED_PEAKS.json. Launches of different views overlap, so the duration used is the timed
          region's wall time per frame times Phase 1's share of the kernel time; the share comes from the "exclusive" pass, which
@@ -212,8 +212,9 @@ def time_path(torch, dist, rm, setups, steps, warmup, device, flush, world_size,
 def time_e2e(torch, dist, cv, rm, poses, steps, warmup, device, world_size, pinned):
     """Public-API path with host buffers: host setup per frame, frames delivered to pinned host memory."""
     def one_step():
-        setups = [rm.make_setup(p) for p in poses]   # RenderManager.DrawWorld's host part, per frame
-        rm.draw_batch(setups, pinned)                 # kernels + device->host frame copies, returns when all frames are on the host
+        # RenderManager.DrawWorld per camera: the host part (LimitRotationHorizon, vanishing point, segments, CameraData) is computed
+        # inside the call from the poses; kernels + device->host frame copies; returns when all frames are on the host
+        rm.draw_world_batch(poses, pinned)
 
     for _ in range(max(1, warmup // 2)):
         one_step()

@@ -472,6 +472,26 @@ int cvx_draw_batch(cvx_ctx* ctx, const cvx_frame_setup* setups, int32_t n_views,
     return CVX_OK;
 }
 
+// RenderManager.DrawWorld for headless hosts (RenderManager.cs:111-194 with UnityManager.LateUpdate's LimitRotationHorizon, UnityManager.cs:181):
+// the per-frame host part (vanishing point, segments, CameraData) is computed here from each pose, then the views go through
+// cvx_draw_batch. One call per batch: no per-view crossing of the FFI boundary.
+int cvx_draw_world_batch(cvx_ctx* ctx, const cvx_pose* poses, int32_t n_views, const float lod_distances[CVX_LOD_LEVELS],
+                         int32_t limit_rotation_horizon, void* dst_frames) {
+    if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
+    if (!poses || n_views < 1 || !lod_distances) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "bad pose batch");
+    if (ctx->world.lod_count <= 0) return fail(ctx, CVX_ERR_NO_WORLD, "no world uploaded");
+    if (ctx->width <= 0) return fail(ctx, CVX_ERR_NO_RESOLUTION, "no resolution set");
+    std::vector<cvx_frame_setup> setups((size_t)n_views);
+    for (int i = 0; i < n_views; i++) {
+        cvx_pose p = poses[i];
+        p.pixel_width = ctx->width; p.pixel_height = ctx->height;   // fakeCamera.pixelRect = (0, 0, resX, resY), UnityManager.cs:180
+        if (limit_rotation_horizon) cvx_host_limit_rotation_horizon(&p);
+        int r = cvx_host_frame_setup(&p, lod_distances, ctx->world.dim_y, &setups[(size_t)i]);
+        if (r) return fail(ctx, r, "frame setup of view %d failed", i);
+    }
+    return cvx_draw_batch(ctx, setups.data(), n_views, dst_frames);
+}
+
 int cvx_sync(cvx_ctx* ctx) {
     if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
     CU(ctx, cudaSetDevice(ctx->device));

@@ -286,6 +286,13 @@ class RenderManager:
         arr = (FrameSetup * len(setups))(*setups)
         self._ck(lib.cvx_draw_batch(self._ctx, arr, len(setups), _ptr(dst) if dst is not None else None))
 
+    def draw_world_batch(self, poses: Sequence[CameraPose], dst: Optional[np.ndarray] = None, limit_horizon: bool = True):
+        """cvx_draw_world_batch: RenderManager.DrawWorld for a batch of cameras — the host part of every view (vanishing point,
+        segments, CameraData) is computed inside the library, one FFI call per batch."""
+        arr = (Pose * len(poses))(*[p.to_native(self.width, self.height) for p in poses])
+        lods = (C.c_float * LOD_LEVELS)(*[float(x) for x in self.lod_distances])
+        self._ck(lib.cvx_draw_world_batch(self._ctx, arr, len(poses), C.byref(lods), int(limit_horizon), _ptr(dst) if dst is not None else None))
+
     def sync(self):
         self._ck(lib.cvx_sync(self._ctx))
 

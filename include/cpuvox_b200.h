@@ -246,6 +246,11 @@ void cvx_host_setup_lods(int32_t world_max_dimension, int32_t res_x, int32_t res
  * GetGenericSegmentParameters x4 (:402-501), CameraData ctor (CameraData.cs:18-36). */
 int cvx_host_frame_setup(const cvx_pose* pose, const float lod_distances[CVX_LOD_LEVELS],
                          int32_t world_dim_y, cvx_frame_setup* out);
+/* RenderManager.DrawWorld for a batch of cameras on a host without UnityEngine (RenderManager.cs:111-194; with limit_rotation_horizon != 0
+ * also UnityManager.LimitRotationHorizon, UnityManager.cs:181): the library computes each view's frame setup from its pose at the
+ * context's resolution (pixel_width / pixel_height of the poses are ignored) and renders the views like cvx_draw_batch. */
+int cvx_draw_world_batch(cvx_ctx* ctx, const cvx_pose* poses, int32_t n_views, const float lod_distances[CVX_LOD_LEVELS],
+                         int32_t limit_rotation_horizon, void* dst_frames);
 /* BenchmarkPath.anim sampled at clip time t in [0, 1.15] (UnityManager.cs:86-87): position is
  * the normalised curve value times the world dimensions; rotation from the Euler curves. */
 void cvx_host_benchmark_pose(float clip_time, const int32_t world_dims[3], cvx_pose* inout_pose);

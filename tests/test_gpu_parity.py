@@ -192,6 +192,25 @@ def test_draw_batch_equals_individual_draws(cv, rm, mill_world):
         rm.set_frames_in_flight(9)
 
 
+def test_draw_world_batch_equals_setup_batch(cv, rm, mill_world):
+    """cvx_draw_world_batch (poses in, host setup inside the library) == cvx_draw_batch of the setups the host computes itself."""
+    rm.upload_world(mill_world)
+    W, H = 320, 180
+    rm.set_resolution(W, H)
+    poses = [pose_for(cv, mill_world, POSES[k]) for k in (0, 3, 4, 7, 9)]   # includes the horizon pose (LimitRotationHorizon applies)
+    setups = [rm.make_setup(p) for p in poses]
+    a = cv.alloc_pinned((len(poses), H, W))
+    b = cv.alloc_pinned((len(poses), H, W))
+    rm.set_counters(False)
+    rm.draw_batch(setups, a)
+    rm.draw_world_batch(poses, b)
+    rm.set_counters(True)
+    assert np.array_equal(a, b)
+    assert (a != 0).all()
+    for x in (a, b):
+        cv.native.lib.cvx_free_pinned(x.ctypes.data)
+
+
 def test_ray_setup_state_matches_oracle(cv, orc, rm, mill_world):
     """RaySetupJob + DDASetupJob + TraceToFirstColumnJob (DrawSegmentRayJob.cs:12-144), including rays that start outside
     the world (StepToWorldIntersection) and rays skybox-filled before the march."""
