@@ -146,3 +146,37 @@ def irregular_world(cv):
     e = int(cells[last])
     cells[last] = (e & 0xFFFF) | ((((e >> 16) & 0xFFFF) + 3) << 16)  # column b: lengths no longer add up to the height
     return cv.World(dims, [blob], [cc], [int((grid != 0).sum())]), blob, cc
+
+
+def random_world_and_cameras(cv, rng, cameras=4):
+    """Fuzz case: a small random world (sparse voxels / heightmap / slabs with gaps; power-of-two dims 8..32, tests/rle.py encoder) and
+    random cameras inside and outside it (any pitch short of vertical, any yaw, sometimes rolled), a random resolution and far clip.
+    Returns (World, blob, column_count, W, H, [CameraPose])."""
+    from rle import encode_world
+    dx, dy, dz = (int(2 ** rng.integers(3, 6)) for _ in range(3))
+    grid = np.zeros((dx, dy, dz), dtype=np.uint32)
+    style = int(rng.integers(0, 3))
+    if style == 0:
+        m = rng.random((dx, dy, dz)) < rng.uniform(0.01, 0.3)
+        grid[m] = rng.integers(1, 2 ** 32 - 1, size=int(m.sum()), dtype=np.uint64).astype(np.uint32) | 0xFF
+    elif style == 1:
+        h = rng.integers(1, dy, size=(dx, dz))
+        for x in range(dx):
+            for z in range(dz):
+                grid[x, :h[x, z], z] = rng.integers(1, 2 ** 32 - 1, dtype=np.uint64).astype(np.uint32) | 0xFF
+    else:
+        for _ in range(int(rng.integers(1, 6))):
+            y0 = int(rng.integers(0, dy))
+            grid[:, y0:y0 + int(rng.integers(1, 4)), :] = rng.integers(1, 2 ** 32 - 1, dtype=np.uint64).astype(np.uint32) | 0xFF
+            x0 = int(rng.integers(0, dx))
+            grid[x0:x0 + 2, :, :] = 0
+    blob, cc = encode_world(grid)
+    world = cv.World((dx, dy, dz), [blob], [cc], [int((grid != 0).sum())])
+    W, H = int(rng.integers(16, 80)), int(rng.integers(16, 80))
+    poses = []
+    for _ in range(cameras):
+        inside = rng.random() < 0.6
+        pos = tuple(float(rng.uniform(0, d)) if inside else float(rng.uniform(-0.5 * d, 1.5 * d)) for d in (dx, dy, dz))
+        euler = (float(rng.uniform(-89.5, 89.5)), float(rng.uniform(0, 360)), float(rng.choice([0.0, 0.0, rng.uniform(-180, 180)])))
+        poses.append(cv.CameraPose.from_euler(pos, euler, far_clip=float(rng.uniform(10, 4 * max(dx, dy, dz)))))
+    return world, blob, cc, W, H, poses

@@ -76,3 +76,17 @@ def test_irregular_world_is_detected_and_general_kernel_matches(cv, orc):
     for pos, eul in [((16.5, 40.5, 2.5), (10, 0, 0)), ((16.5, 70.5, 16.5), (75, 30, 0)), ((3.5, 20.5, 3.5), (-30, 45, 0))]:
         s = cv.frame_setup(cv.CameraPose.from_euler(pos, eul, far_clip=100.0), W, H, lods, world.dims[1])
         _check(cv, orc, ow, ew, s, W, H, f"irregular {pos} {eul}", variants=(0,))
+
+
+def test_emulated_kernels_fuzz(cv, orc):
+    """Seeded fuzz of the kernel logic on the CPU: random small worlds and cameras, both kernels, against the oracle."""
+    from conftest import random_world_and_cameras
+    rng = np.random.default_rng(99)
+    lods = np.full(6, 1e9, dtype=np.float32)
+    for it in range(12):
+        world, blob, cc, W, H, poses = random_world_and_cameras(cv, rng, cameras=2)
+        ow = orc.OracleWorld(world.dims, [blob], [cc])
+        ew = emu.EmuWorld(world)
+        for k, pose in enumerate(poses):
+            s = cv.frame_setup(pose, W, H, lods, world.dims[1])
+            _check(cv, orc, ow, ew, s, W, H, f"fuzz world {it} {world.dims} {W}x{H} camera {k}", variants=(0, 1) if ew.regular else (0,))

@@ -469,3 +469,20 @@ def test_structure_world_8k_and_batched_cameras_configs_4_5(cv, orc, rm):
         o = _oracle_frame(orc, ow, s, W, H, 0)
         assert np.array_equal(dst[i], o[3]), f"batched camera {i}"
     cv.native.lib.cvx_free_pinned(dst.ctypes.data)
+
+
+def test_fuzz_random_worlds_and_cameras(cv, orc, rm):
+    """Seeded fuzz through the C ABI: 300 random small worlds x 4 random cameras (inside geometry, outside the world, steep, rolled,
+    random resolution and far clip) — raybuffers, counters and frame bit-exact against the oracle, product and counter builds and
+    the general kernel included (_gpu_frame)."""
+    from conftest import random_world_and_cameras
+    rng = np.random.default_rng(424242)
+    lods = np.full(6, 1e9, dtype=np.float32)
+    for it in range(300):
+        world, blob, cc, W, H, poses = random_world_and_cameras(cv, rng)
+        ow = orc.OracleWorld(world.dims, [blob], [cc])
+        rm.upload_world(world)
+        rm.set_resolution(W, H)
+        for k, pose in enumerate(poses):
+            s = cv.frame_setup(pose, W, H, lods, world.dims[1])
+            _assert_same(_gpu_frame(rm, s, MAGENTA), _oracle_frame(orc, ow, s, W, H, MAGENTA), f"fuzz world {it} {world.dims} {W}x{H} camera {k}")
