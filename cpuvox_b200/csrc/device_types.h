@@ -8,8 +8,10 @@
 
 #define CVXD_LODS 6
 #define CVXD_MAX_AXIS 8192          /* longest raybuffer row (max(W,H)) the seen-mask in shared memory supports */
+/* Phase 1 runs one warp (one ray at the default group width) per CTA: a CTA of several warps lives as long as its slowest ray and
+ * keeps the other warps' slots idle; with 96 registers or fewer per thread 21+ such CTAs are resident per SM (profiles/r01e). */
 #ifndef CVXD_THREADS_PER_CTA
-#define CVXD_THREADS_PER_CTA 128
+#define CVXD_THREADS_PER_CTA 32
 #endif
 #define CVXD_TIMING_REGIONS 16
 

@@ -330,14 +330,23 @@ __device__ __forceinline__ void touch(const uint32_t* p) {
  * Neighbouring rows (adjacent rays of one segment) share a warp: they walk nearly the same columns, so the groups of
  * a warp stay mostly convergent while the number of rays in flight per SM grows by 32/G.
  */
-#ifndef CVXD_HULL
-#define CVXD_HULL 1
+#ifndef CVXD_HOT_SKIP /* skip cached columns none of whose lanes can still write (exact, from the hot-lane masks) */
+#define CVXD_HOT_SKIP 1
+#endif
+#ifndef CVXD_HULL /* hull test for columns that are not in the round cache: since the hot-lane masks it costs more than it saves (off) */
+#define CVXD_HULL 0
+#endif
+#ifndef CVXD_TOUCH /* prefetch of each non-empty column's first boundary record at batch time: neutral since the round cache (off) */
+#define CVXD_TOUCH 0
+#endif
+#ifndef CVXD_DEFER_STORE /* store of a side-span pixel deferred to the next gather: neutral, costs two registers (off) */
+#define CVXD_DEFER_STORE 0
 #endif
 #ifndef CVXD_MULTI_COL
 #define CVXD_MULTI_COL 1
 #endif
-#ifndef CVXD_MIN_CTAS_PER_SM
-#define CVXD_MIN_CTAS_PER_SM 4
+#ifndef CVXD_MIN_CTAS_PER_SM /* with 32-thread CTAs: 21 -> ptxas settles on 80 registers (25 resident warps per SM); measured best */
+#define CVXD_MIN_CTAS_PER_SM 21
 #endif
 template <int G, bool COUNTERS, bool TIMING, bool FAST, bool INV>
 __global__ void __launch_bounds__(CVXD_THREADS_PER_CTA, CVXD_MIN_CTAS_PER_SM)
@@ -491,7 +500,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
             if (gl < n) hdr = __ldg(world.lods[myLod].headers + myIdx);
             const bool myNonEmpty = (hdr.y & 0xffffu) != 0u;
             // start fetching the run list of every non-empty column of the batch now; the column bodies below find it cached
-            if (myNonEmpty) {
+            if (CVXD_TOUCH && myNonEmpty) {
                 if (FAST) touch((const uint32_t*)(world.lods[myLod].bounds + hdr.w + (ITER > 0 ? 0u : (hdr.y & 0xffffu))));
                 else touch(world.lods[myLod].elements + hdr.x + (ITER > 0 ? 1u : (hdr.y & 0xffffu)));
             }
@@ -557,9 +566,9 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                     const bool culled = myWorldMin > newMax || myWorldMax < newMin;   // column outside the writable world bounds
                     // cannot write, hence no side effects: exactly known for a column in the round cache, by its hull otherwise
                     bool inert = false;
-                    if (CVXD_HULL && !COUNTERS && !culled && myNonEmpty) {
-                        if ((roundCols >> gl) & 1u) inert = !((roundHotS | roundHotC) & ((myRunCount >= 32 ? FULL_MASK : ((1u << myRunCount) - 1u)) << myBase));
-                        else inert = !span_would_write(rw, hullMin, hullMax);
+                    if ((CVXD_HULL || CVXD_HOT_SKIP) && !COUNTERS && !culled && myNonEmpty) {
+                        if (CVXD_HOT_SKIP && ((roundCols >> gl) & 1u)) inert = !((roundHotS | roundHotC) & ((myRunCount >= 32 ? FULL_MASK : ((1u << myRunCount) - 1u)) << myBase));
+                        else if (CVXD_HULL) inert = !span_would_write(rw, hullMin, hullMax);
                     }
                     const uint32_t cand = GBALLOT(myNonEmpty && (outOfWorld || !(culled || inert))) & remaining;
                     if (!cand) {
@@ -945,8 +954,10 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                                         float u = wy / wx;
                                         idx = max(0, min(jLen - 1, f2i(floorf(u)))) + jCi;
                                     }
-                                    if (pendY >= 0) row[pendY] = pendColor; // the gather issued by the previous commit has long arrived
-                                    pendColor = __ldg(colColors + idx); pendY = y;
+                                    if (CVXD_DEFER_STORE) {
+                                        if (pendY >= 0) row[pendY] = pendColor; // the gather issued by the previous commit has long arrived
+                                        pendColor = __ldg(colColors + idx); pendY = y;
+                                    } else row[y] = __ldg(colColors + idx);
                                 }
                             }
                         }

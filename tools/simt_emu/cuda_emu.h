@@ -136,6 +136,11 @@ template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline int __ffs(unsigned x) { return x ? __builtin_ctz(x) + 1 : 0; }
 static inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline unsigned __fns(unsigned mask, unsigned base, int offset) { // position of the offset-th set bit at or above base (offset > 0), 0xffffffff if none
+    if (offset <= 0) return 0xffffffffu; // (negative / zero offsets are not used by the kernels)
+    for (unsigned i = base; i < 32; i++) if ((mask >> i) & 1u) { if (--offset == 0) return i; }
+    return 0xffffffffu;
+}
 static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) { // prmt.b32, default mode: nibble i of sel picks a byte of {b,a}
     const unsigned long long pool = ((unsigned long long)b << 32) | a;
     unsigned r = 0;
