@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--res", default="3840x2160")
     ap.add_argument("--maxdim", type=int, default=1024)
     ap.add_argument("--group", type=int, default=0, help="Phase-1 lanes per ray (0 = library default)")
-    ap.add_argument("--inflight", type=int, default=4, help="views in flight per cvx_draw_batch (1..8)")
+    ap.add_argument("--inflight", type=int, default=6, help="views in flight per cvx_draw_batch (1..8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-1080p", action="store_true")
     return ap.parse_args()

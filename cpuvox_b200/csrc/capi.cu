@@ -24,7 +24,7 @@ static_assert(sizeof(cvx_counters) == sizeof(cvxd_counters), "counter layout");
 static_assert(CVX_LOD_LEVELS == CVXD_LODS, "lod levels");
 
 #define CVX_MAX_SLOTS 8
-#define CVX_DEFAULT_SLOTS 4
+#define CVX_DEFAULT_SLOTS 6
 
 struct cvx_slot {
     cudaStream_t stream = nullptr;

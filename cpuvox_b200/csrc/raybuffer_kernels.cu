@@ -202,39 +202,30 @@ __device__ void setup_ray(const cvxd_world& world, const cvxd_frame& f, int flat
 }
 
 // ---- written-pixel bitmask helpers -------------------------------------------------------------------------
-// Two levels in shared memory: seen[w] has one bit per pixel of the row, full[w >> 5] has bit (w & 31) set when seen[w] is
-// all ones. Scans and range tests hop over fully written stretches through the second level (at most 8 words at 8K).
+// One bit per pixel of the row in shared memory (the README's "bitmask"; the reference keeps a byte per pixel, :208). A second
+// level (one bit per fully written word) was measured slower once the screen-hull test was dropped: spans and horizon scans touch one
+// or two words, and the extra bookkeeping (a shared atomic per completed word, ~350 SASS instructions) cost 5 % (profiles/r01e).
 // bits [a & 31 .. 31] of the word holding a, and bits [0 .. b & 31] of the word holding b
 __device__ __forceinline__ uint32_t mask_from(int a) { return FULL_MASK << (a & 31); }
 __device__ __forceinline__ uint32_t mask_to(int b) { return FULL_MASK >> (31 - (b & 31)); }
 
 // index of the first word in [wlo, whi] that is not fully written, or whi + 1
-__device__ __forceinline__ int next_open_word(const uint32_t* full, int wlo, int whi) {
-    int w = wlo;
-    while (w <= whi) {
-        const uint32_t m = ~full[w >> 5] & mask_from(w);
-        if (m) { const int r = (w & ~31) + __ffs(m) - 1; return r <= whi ? r : whi + 1; }
-        w = (w & ~31) + 32;
-    }
+__device__ __forceinline__ int next_open_word(const uint32_t* seen, int wlo, int whi) {
+    for (int w = wlo; w <= whi; w++) if (~seen[w]) return w;
     return whi + 1;
 }
 // index of the last word in [wlo, whi] that is not fully written, or wlo - 1
-__device__ __forceinline__ int prev_open_word(const uint32_t* full, int wlo, int whi) {
-    int w = whi;
-    while (w >= wlo) {
-        const uint32_t m = ~full[w >> 5] & mask_to(w);
-        if (m) { const int r = (w & ~31) + 31 - __clz(m); return r >= wlo ? r : wlo - 1; }
-        w = (w & ~31) - 1;
-    }
+__device__ __forceinline__ int prev_open_word(const uint32_t* seen, int wlo, int whi) {
+    for (int w = whi; w >= wlo; w--) if (~seen[w]) return w;
     return wlo - 1;
 }
 // first index >= start whose bit is clear, at most limit+1  ("while (i <= limit && seen[i]) i++")
-__device__ __forceinline__ int scan_up(const uint32_t* seen, const uint32_t* full, int start, int limit) {
+__device__ __forceinline__ int scan_up(const uint32_t* seen, int start, int limit) {
     if (start > limit) return start;
     uint32_t x = ~seen[start >> 5] & mask_from(start);
     int w = start >> 5;
     if (!x) {
-        w = next_open_word(full, w + 1, limit >> 5);
+        w = next_open_word(seen, w + 1, limit >> 5);
         if (w > (limit >> 5)) return limit + 1;
         x = ~seen[w];
     }
@@ -242,12 +233,12 @@ __device__ __forceinline__ int scan_up(const uint32_t* seen, const uint32_t* ful
     return j <= limit ? j : limit + 1;
 }
 // last index <= start whose bit is clear, at least limit-1  ("while (i >= limit && seen[i]) i--")
-__device__ __forceinline__ int scan_down(const uint32_t* seen, const uint32_t* full, int start, int limit) {
+__device__ __forceinline__ int scan_down(const uint32_t* seen, int start, int limit) {
     if (start < limit) return start;
     uint32_t x = ~seen[start >> 5] & mask_to(start);
     int w = start >> 5;
     if (!x) {
-        w = prev_open_word(full, limit >> 5, w - 1);
+        w = prev_open_word(seen, limit >> 5, w - 1);
         if (w < (limit >> 5)) return limit - 1;
         x = ~seen[w];
     }
@@ -255,15 +246,15 @@ __device__ __forceinline__ int scan_down(const uint32_t* seen, const uint32_t* f
     return j >= limit ? j : limit - 1;
 }
 // any clear bit in [a, b] (a <= b, both inside the row)
-__device__ __forceinline__ bool any_unseen(const uint32_t* seen, const uint32_t* full, int a, int b) {
+__device__ __forceinline__ bool any_unseen(const uint32_t* seen, int a, int b) {
     const int wa = a >> 5, wb = b >> 5;
     if (wa == wb) return (~seen[wa] & mask_from(a) & mask_to(b)) != 0u;
     if ((~seen[wa] & mask_from(a)) | (~seen[wb] & mask_to(b))) return true;
-    return wa + 1 < wb && next_open_word(full, wa + 1, wb - 1) < wb;
+    return wa + 1 < wb && next_open_word(seen, wa + 1, wb - 1) < wb;
 }
 // mark [a, b] written: lane `gl` of G handles every G-th word; returns how many of them were new (for the counters)
 template <int G>
-__device__ __forceinline__ int mark_seen(uint32_t* seen, uint32_t* full, int a, int b, int gl) {
+__device__ __forceinline__ int mark_seen(uint32_t* seen, int a, int b, int gl) {
     int fresh = 0;
     for (int w = (a >> 5) + gl; w <= (b >> 5); w += G) {
         uint32_t m = FULL_MASK;
@@ -272,14 +263,12 @@ __device__ __forceinline__ int mark_seen(uint32_t* seen, uint32_t* full, int a, 
         const uint32_t old = seen[w], now = old | m;
         fresh += __popc(~old & m);
         seen[w] = now;
-        if (now == FULL_MASK && old != FULL_MASK) atomicOr(&full[w >> 5], 1u << (w & 31));
     }
     return fresh;
 }
 
 struct RowState {
     uint32_t* seen;         // shared-memory bitmask of this row
-    uint32_t* full;         // second level: one bit per word of `seen` that is all ones
     uint32_t* row;          // raybuffer row
     int orig_min, orig_max; // originalNextFreePixelMin/Max
     int nf_min, nf_max;     // nextFreePixelMin/Max
@@ -293,7 +282,7 @@ struct RowState {
 __device__ __forceinline__ bool span_would_write(const RowState& rw, int bMin, int bMax) {
     if (!(bMax >= rw.nf_min && bMin <= rw.nf_max)) return false;
     const int a = bMin > rw.nf_min ? bMin : rw.nf_min, b = bMax < rw.nf_max ? bMax : rw.nf_max;
-    return a <= b && any_unseen(rw.seen, rw.full, a, b);
+    return a <= b && any_unseen(rw.seen, a, b);
 }
 
 // ReducePixelHorizon :660-697 (uniform across the group)
@@ -301,14 +290,14 @@ __device__ __forceinline__ void reduce_pixel_horizon(RowState& rw, int& bMin, in
     if (bMin <= rw.nf_min) {
         bMin = rw.nf_min;
         if (bMax >= rw.nf_min) {
-            rw.nf_min = scan_up(rw.seen, rw.full, bMax + 1, rw.orig_max);
+            rw.nf_min = scan_up(rw.seen, bMax + 1, rw.orig_max);
             rw.fb_min = rw.nf_min - 0.501f;
         }
     }
     if (bMax >= rw.nf_max) {
         bMax = rw.nf_max;
         if (bMin <= rw.nf_max) {
-            rw.nf_max = scan_down(rw.seen, rw.full, bMin - 1, rw.orig_min);
+            rw.nf_max = scan_down(rw.seen, bMin - 1, rw.orig_min);
             rw.fb_max = rw.nf_max + 0.501f;
         }
     }
@@ -385,10 +374,8 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
     Acc acc = {0, 0, 0, 0, 0}; // per lane; summed with atomics at the end (COUNTERS only)
     if (COUNTERS && gl == 0) acc.dda_steps = (unsigned long long)rs.lod_steps;
     RowState rw;
-    const int fullWords = (seenWords + 31) >> 5;
-    rw.seen = seen_all + group * (seenWords + fullWords + 9 * G);
-    rw.full = rw.seen + seenWords;
-    int* scratch = (int*)(rw.full + fullWords); // G ints: lane of a round -> batch cell of its column
+    rw.seen = seen_all + group * (seenWords + 9 * G);
+    int* scratch = (int*)(rw.seen + seenWords); // G ints: lane of a round -> batch cell of its column
     uint32_t* cache = (uint32_t*)(scratch + G); // 8 x G words: commit-only fields of the round cache
     rw.row = row;
     rw.orig_min = sg.pix_min; rw.orig_max = sg.pix_max;
@@ -399,7 +386,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
         for (int y = rw.orig_min + gl; y <= rw.orig_max; y += G) row[y] = SKYBOX_ARGB;
         if (COUNTERS && gl == 0 && rw.orig_max >= rw.orig_min) acc.px_sky += rw.orig_max - rw.orig_min + 1;
     } else {
-        for (int w = gl; w < seenWords + fullWords; w += G) rw.seen[w] = 0u; // stackalloc, zero-initialised (:208); both levels
+        for (int w = gl; w < seenWords; w += G) rw.seen[w] = 0u; // stackalloc, zero-initialised (:208)
         __syncwarp(gmask);
 
         Dda ray = rs.dda;
@@ -650,8 +637,8 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                     const int writableMin = f2i(floorf(clippedMin));
                     const int writableMax = f2i(ceilf(clippedMax));
                     if (writableMax < rw.nf_min || writableMin > rw.nf_max) { terminated = true; cellsDone = c + 1; break; }
-                    if (writableMin > rw.nf_min) rw.nf_min = scan_up(rw.seen, rw.full, writableMin, rw.orig_max);
-                    if (writableMax < rw.nf_max) rw.nf_max = scan_down(rw.seen, rw.full, writableMax, rw.orig_min);
+                    if (writableMin > rw.nf_min) rw.nf_min = scan_up(rw.seen, writableMin, rw.orig_max);
+                    if (writableMax < rw.nf_max) rw.nf_max = scan_down(rw.seen, writableMax, rw.orig_min);
                     if (rw.nf_min > rw.nf_max) { terminated = true; cellsDone = c + 1; break; }
                 }
 
@@ -963,7 +950,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                         }
                         STAMP(13);
                         __syncwarp(gmask);
-                        { const int fresh = mark_seen<G>(rw.seen, rw.full, bMin, bMax, gl); if (COUNTERS) acc.px_voxel += fresh; }
+                        { const int fresh = mark_seen<G>(rw.seen, bMin, bMax, gl); if (COUNTERS) acc.px_voxel += fresh; }
                         __syncwarp(gmask);
                         STAMP(6);
                         frustumDirMaxWorld = EPS; // a pixel was written (:522,598)
@@ -1125,7 +1112,7 @@ static cudaError_t launch_phase1_g(const cvxd_world& world, const cvxd_frame& fr
     constexpr int groupsPerCta = CVXD_THREADS_PER_CTA / G;
     const int blocks = (n + groupsPerCta - 1) / groupsPerCta;
     const int seenWords = ((frame.width > frame.height ? frame.width : frame.height) + 31) >> 5;
-    const size_t smem = (size_t)groupsPerCta * (seenWords + ((seenWords + 31) >> 5) + 9 * G) * sizeof(uint32_t);
+    const size_t smem = (size_t)groupsPerCta * (seenWords + 9 * G) * sizeof(uint32_t);
     // FAST: the boundary-table kernel, for regular worlds (world_transcode.h)
     const bool fast = world.regular && !frame.general_path;
 #define CVXD_P1(C, T, F) do { \

@@ -168,7 +168,7 @@ int64_t cvx_launch_count(const cvx_ctx* ctx);
  *   CVX_OPT_COUNTERS    1 = accumulate cvx_counters (same as CVX_FLAG_COUNTERS at creation), 0 = off.
  *   CVX_OPT_GENERAL_PATH 1 = always run the general Phase-1 kernel (reads the reference element area run by run); 0 (default) =
  *                       use the boundary-table kernel whenever the uploaded world is regular (see cvx_world_is_regular).
- *   CVX_OPT_FRAMES_IN_FLIGHT 1..8 (default 4): views of one cvx_draw_batch rendered concurrently, each on its own stream with its
+ *   CVX_OPT_FRAMES_IN_FLIGHT 1..8 (default 6): views of one cvx_draw_batch rendered concurrently, each on its own stream with its
  *                       own raybuffers and framebuffer (the reference double-buffers its raybuffers for the same reason,
  *                       RenderManager.cs:14,53-56). Extra buffer sets are allocated on the first batch that needs them. */
 #define CVX_OPT_GROUP_SIZE 1

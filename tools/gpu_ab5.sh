@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-bash tools/ab.sh nofns 2>&1 | tee gpurun_out/ab_feat.log
-bash tools/ab.sh nofns 2>&1 | tee -a gpurun_out/ab_feat.log
+bash tools/ab.sh nohot m20 m24 2>&1 | tee gpurun_out/ab_feat.log
