@@ -325,6 +325,9 @@ __device__ __forceinline__ void touch(const uint32_t* p) {
 #ifndef CVXD_HULL /* hull test for columns that are not in the round cache: since the hot-lane masks it costs more than it saves (off) */
 #define CVXD_HULL 0
 #endif
+#ifndef CVXD_FOLLOW_CULL /* leave columns the current frustum culls out of a new round: measured slightly negative (off) */
+#define CVXD_FOLLOW_CULL 0
+#endif
 #ifndef CVXD_TOUCH /* prefetch of each non-empty column's first boundary record at batch time: neutral since the round cache (off) */
 #define CVXD_TOUCH 0
 #endif
@@ -337,8 +340,13 @@ __device__ __forceinline__ void touch(const uint32_t* p) {
 #ifndef CVXD_MIN_CTAS_PER_SM /* with 32-thread CTAs: 21 -> ptxas settles on 80 registers (25 resident warps per SM); measured best */
 #define CVXD_MIN_CTAS_PER_SM 21
 #endif
+#if CVXD_MIN_CTAS_PER_SM > 0
+#define CVXD_P1_BOUNDS __launch_bounds__(CVXD_THREADS_PER_CTA, CVXD_MIN_CTAS_PER_SM)
+#else /* variants built with -maxrregcount */
+#define CVXD_P1_BOUNDS
+#endif
 template <int G, bool COUNTERS, bool TIMING, bool FAST, bool INV>
-__global__ void __launch_bounds__(CVXD_THREADS_PER_CTA, CVXD_MIN_CTAS_PER_SM)
+__global__ void CVXD_P1_BOUNDS
 phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ cvxd_frame f) {
 #ifdef CVX_EMU
     uint32_t* seen_all = emu::g_shared;
@@ -660,7 +668,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                         // prefix sum), and the projected side/cap spans — the float-heavy part — once for all of them.
                         EMU_STAT(4); // rounds formed
                         uint32_t follow = (CVXD_MULTI_COL && !tall) ? remaining : 0u;
-                        if (follow && frustumDirMaxWorld != EPS) {
+                        if (CVXD_FOLLOW_CULL && follow && frustumDirMaxWorld != EPS) {
                             const float distTop = frustumDirMaxWorld > 0.0f ? myDn : myDl;
                             const float distBot = frustumDirMinWorld < 0.0f ? myDn : myDl;
                             const float newMax = camY + frustumDirMaxWorld * distTop;

@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-bash tools/ab.sh nohot m20 m24 2>&1 | tee gpurun_out/ab_feat.log
+bash tools/ab.sh r88 r72 r96 2>&1 | tee gpurun_out/ab_feat.log
