@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--maxdim", type=int, default=1024)
     ap.add_argument("--group", type=int, default=0, help="Phase-1 lanes per ray (0 = library default)")
     ap.add_argument("--inflight", type=int, default=6, help="views in flight per cvx_draw_batch (1..8)")
+    ap.add_argument("--inflight-e2e", type=int, default=8, help="views in flight for the e2e leg (frame copies occupy the slots longer)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-1080p", action="store_true")
     return ap.parse_args()
@@ -288,7 +289,9 @@ def run_b200(a, rank, local_rank, world_size):
         _, x1, x2, xn, _, _ = time_path(torch, dist, rm, setups, 1, 1, device, flush, world_size)
         rm.set_frames_in_flight(a.inflight)
         pinned = cv.alloc_pinned((len(poses), h, w))
+        rm.set_frames_in_flight(a.inflight_e2e)   # a slot is busy with its device->host copy too: more slots keep the GPU fed
         e2e_s = time_e2e(torch, dist, cv, rm, poses, steps, a.warmup, device, world_size, pinned)
+        rm.set_frames_in_flight(a.inflight)
         N.lib.cvx_free_pinned(pinned.ctypes.data)
         t = torch.tensor([ms, e2e_s * 1000.0, p1, p2, x1, x2], dtype=torch.float64, device=f"cuda:{device}")
         if world_size > 1:
@@ -338,7 +341,7 @@ def run_b200(a, rank, local_rank, world_size):
             "workload": workload_name(a.maxdim, W, H), "resolution": [W, H], "frames_per_step": FRAMES_PER_STEP * world_size,
             "parallelism": "1 GPU" if world_size == 1 else f"views sharded over {world_size} GPUs, world broadcast once and replicated, no data-path collective",
             "l2": "flushed between steps (256 MiB device write inside the timed region); frames of one step run back to back",
-            "phase1_lanes_per_ray": a.group or 32, "frames_in_flight": a.inflight,
+            "phase1_lanes_per_ray": a.group or 32, "frames_in_flight": a.inflight, "frames_in_flight_e2e": a.inflight_e2e,
         },
         "runs_per_s": runs_per_frame * fps,
         "ms_per_frame": {"total": frame_ms, "phase1_kernel": p1_ms, "phase2_kernel": p2_ms,
