@@ -63,6 +63,14 @@ public static unsafe class CpuVoxB200
 	[DllImport(LIB)] public static extern int cvx_get_counters(IntPtr ctx, out Counters counters, int reset);
 	[DllImport(LIB)] public static extern int cvx_device_frame(IntPtr ctx, out IntPtr devicePtr, out long bytes);
 	[DllImport(LIB)] public static extern int cvx_clear_raybuffers(IntPtr ctx, uint argb);
+	[DllImport(LIB)] public static extern int cvx_set_option(IntPtr ctx, int option, int value); // 1 lanes per ray, 2 counters, 3 general path, 4 views in flight
+	// world production on the GPU (VoxelizerHelper + WorldBuilder.ToFinalColumn + World.DownSample as CUDA kernels); positions = n x float3
+	// already in mesh space, colors32 = n x Color32; flips = int[3]. The first returns a builder handle (read its LOD blobs with
+	// cvx_builder_lod, free with cvx_builder_free), the second installs the result as the context's world without a host copy.
+	[DllImport(LIB)] public static extern int cvx_gpu_builder_from_mesh(IntPtr ctx, float* positions, byte* colors32, int nVertices, int maxDimension, int* flips, int nLods, out IntPtr builder);
+	[DllImport(LIB)] public static extern int cvx_world_build_from_mesh(IntPtr ctx, float* positions, byte* colors32, int nVertices, int maxDimension, int* flips, int nLods, int* outDims, long* outVoxelCounts);
+	[DllImport(LIB)] public static extern int cvx_builder_lod(IntPtr builder, int lod, out IntPtr blob, out long bytes, out int columnCount, out long voxelCount);
+	[DllImport(LIB)] public static extern void cvx_builder_free(IntPtr builder);
 	[DllImport(LIB)] public static extern int cvx_blit_raybuffer(IntPtr ctx, int which); // ERenderMode.RayBufferTopDown (0) / RayBufferLeftRight (1), UnityManager.cs:471-483
 	[DllImport(LIB)] public static extern int cvx_present(IntPtr ctx, int format, int topDown, void* dst, int dstIsDevice); // 0 = RGBA8, 1 = BGRA8
 
