@@ -105,6 +105,7 @@ int validate_setup(cvx_ctx* ctx, const cvx_frame_setup* s, int total) {
 
 void make_frame(cvx_ctx* ctx, const cvx_frame_setup* s, cvxd_frame& f) {
     cvxh::frame_from_setup(s, ctx->width, ctx->height, f);
+    cvxd_frame_set_world(&f, &ctx->world);
     f.td = ctx->td; f.lr = ctx->lr;
     f.counters = (ctx->flags & CVX_FLAG_COUNTERS) ? ctx->counters : nullptr;
     f.general_path = ctx->generalPath;
@@ -207,7 +208,7 @@ int install_lod(cvx_ctx* ctx, int lod, int dim_x, int dim_y, int dim_z, void* db
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->lodHeaders[lod]); cudaFree(ctx->lodElements[lod]); cudaFree(ctx->lodBounds[lod]);
     ctx->lodHeaders[lod] = headers; ctx->lodElements[lod] = dblob; ctx->lodBounds[lod] = bounds;
-    ctx->world.dim_x = dim_x; ctx->world.dim_y = dim_y; ctx->world.dim_z = dim_z;
+    cvxd_world_set_dims(&ctx->world, dim_x, dim_y, dim_z);
     cvxd_lod& l = ctx->world.lods[lod];
     l.headers = (const uint4*)headers;
     l.elements = (const uint32_t*)((const uint8_t*)dblob + headerBytes); // the reference element area, verbatim

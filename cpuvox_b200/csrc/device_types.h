@@ -37,7 +37,16 @@ struct cvxd_world {
     int32_t dim_x, dim_y, dim_z;
     int32_t lod_count;
     int32_t regular;    /* every uploaded LOD consists of full-height columns of valid runs: `bounds` may be used */
+    /* derived on the host so that the kernels read them as constant-bank operands instead of holding them in registers */
+    float dim_y_f;      /* (float)dim_y = worldMaxY (DrawSegmentRayJob.cs:213) */
+    float inv_dim_y;    /* 1 / dim_y, exact when dim_y is a power of two */
+    int32_t y_pow2;     /* dim_y is a power of two: unlerp(0, worldMaxY, y) == y * inv_dim_y exactly */
 };
+
+static inline void cvxd_world_set_dims(cvxd_world* w, int dx, int dy, int dz) {
+    w->dim_x = dx; w->dim_y = dy; w->dim_z = dz;
+    w->dim_y_f = (float)dy; w->inv_dim_y = 1.0f / (float)dy; w->y_pow2 = (dy & (dy - 1)) == 0 ? 1 : 0;
+}
 
 /* DrawSegmentRayJob.SegmentContext (Assets/Code/Rendering/DrawSegmentRayJob.cs:718-727) minus the pointers. */
 struct cvxd_segment {
@@ -59,6 +68,7 @@ struct cvxd_frame {
     float pos_x, pos_z, pos_y;
     int32_t inverse;                /* InverseElementIterationDirection */
     float far_clip;
+    float cam_y_norm;               /* PositionY / worldMaxY (DrawSegmentRayJob.cs:214), set with cvxd_frame_set_world */
     float lod_dist[CVXD_LODS];
     cvxd_segment seg[4];
     float vp_x, vp_y;
@@ -83,6 +93,8 @@ struct cvxd_blit {
     const uint32_t* lr;
     uint32_t* frame;
 };
+
+static inline void cvxd_frame_set_world(cvxd_frame* f, const cvxd_world* w) { f->cam_y_norm = f->pos_y / w->dim_y_f; }
 
 struct cvxd_ray_state { /* mirrors cvx_ray_state */
     int32_t segment, plane_ray_index, status, lod;

@@ -402,9 +402,9 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
         int voxelScale = 1 << lod;
         const float farClip = f.far_clip;
         float lodMax = f.lod_dist[lod];
-        const float worldMaxY = (float)world.dim_y;
+        #define worldMaxY (world.dim_y_f) /* a constant-bank operand, not a register */
         const float camY = f.pos_y;
-        const float cameraPosYNormalized = camY / worldMaxY;
+        #define cameraPosYNormalized (f.cam_y_norm)
         constexpr int ITER = INV ? -1 : 1; // RenderJob.Execute :174-178 (INV = InverseElementIterationDirection, one kernel instance per direction)
         const float EPS = float_epsilon();
         float frustumDirMaxWorld = EPS, frustumDirMinWorld = EPS;
@@ -423,8 +423,6 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
         }
         const int maskX = world.dim_x - 1, maskZ = world.dim_z - 1;
         // unlerp(0, worldMaxY, y) = (y - 0) / (worldMaxY - 0): for a power-of-two height the quotient is exactly y * 2^-k
-        const bool yPow2 = (world.dim_y & (world.dim_y - 1)) == 0;
-        const float invWorldMaxY = 1.0f / worldMaxY;
 
         // Side-span pixels are a colour gather followed by a store: the store is deferred until this lane's next gather (or the end
         // of the ray), so the gather's latency is not on the ray's critical path. Nothing in this kernel reads the row back.
@@ -722,7 +720,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                             const F3 lMinNext = F3{planeBottom.x + planeDir.x * cDn, planeBottom.y + planeDir.y * cDn, planeBottom.z + planeDir.z * cDn};
                             const F3 lMaxLast = F3{planeTop.x + planeDir.x * cDl, planeTop.y + planeDir.y * cDl, planeTop.z + planeDir.z * cDl};
                             const F3 lMaxNext = F3{planeTop.x + planeDir.x * cDn, planeTop.y + planeDir.y * cDn, planeTop.z + planeDir.z * cDn};
-                            const float portion = yPow2 ? (float)yB * invWorldMaxY : unlerpf(0.0f, worldMaxY, (float)yB); // :478-479
+                            const float portion = world.y_pow2 ? (float)yB * world.inv_dim_y : unlerpf(0.0f, worldMaxY, (float)yB); // :478-479
                             const F3 Fp = lerp3(lMinLast, lMaxLast, portion), Np = lerp3(lMinNext, lMaxNext, portion);
                             bFx = Fp.x; bFy = Fp.y; bFz = Fp.z;
                             const bool fFront = !(Fp.y <= 0.0f), nFront = !(Np.y <= 0.0f); // in front of the near plane (CameraData.cs:126,143)
@@ -1003,6 +1001,8 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
     }
 #undef GBALLOT
 #undef GSHFL
+#undef worldMaxY
+#undef cameraPosYNormalized
 }
 
 // ---- Phase 2 -----------------------------------------------------------------------------------------------

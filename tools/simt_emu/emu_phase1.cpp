@@ -49,7 +49,7 @@ extern "C" {
 emu_world* emu_world_create(int lods, const int32_t dims[3], const void* const* blobs, const int64_t* bytes, const int32_t* column_counts) {
     emu_world* w = new emu_world();
     memset(&w->w, 0, sizeof w->w);
-    w->w.dim_x = dims[0]; w->w.dim_y = dims[1]; w->w.dim_z = dims[2];
+    cvxd_world_set_dims(&w->w, dims[0], dims[1], dims[2]);
     w->w.lod_count = lods;
     w->w.regular = 1;
     for (int l = 0; l < lods; l++) {
@@ -80,6 +80,7 @@ int emu_phase1(const emu_world* w, const cvx_frame_setup* setup, int W, int H, u
                int variant, int group, int threads, int ray_begin, int ray_end) {
     cvxd_frame f;
     cvxh::frame_from_setup(setup, W, H, f);
+    cvxd_frame_set_world(&f, &w->w);
     f.td = td; f.lr = lr; f.counters = counters;
     if (ray_end < 0 || ray_end > f.total_rays) ray_end = f.total_rays;
     if (ray_begin < 0) ray_begin = 0;
