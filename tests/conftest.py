@@ -18,7 +18,7 @@ if ROOT not in sys.path:
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     # build the product library and the oracle once per session (nvcc cross-compiles without a GPU)
-    subprocess.check_call(["make", "-C", os.path.join(ROOT, "cpuvox_b200", "csrc"), "-s"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "cpuvox_b200", "csrc"), "-s", "-j4"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
