@@ -67,6 +67,17 @@ def orc():
 
 
 @pytest.fixture(scope="session")
+def ref():
+    """oracle/_ref: the reference's own C# sources translated to C++ and compiled (oracle/ref.py). Built here from
+    /root/reference; on the GPU box the prebuilt .so travels with the snapshot."""
+    from oracle import ref as r
+    if r.build() is None:
+        pytest.skip("oracle/_ref/libcpuvox_ref.so absent and /root/reference not available to build it")
+    r.lib()
+    return r
+
+
+@pytest.fixture(scope="session")
 def terrain_world(cv):
     """Seeded fBm heightmap shell (BASELINE config 2 generator at test size)."""
     return cv.World.synthetic(0, (256, 256, 256), seed=1234)
@@ -88,6 +99,30 @@ def pose_for(cv, world, spec, far_scale=2.0):
     _, euler, frac = spec
     pos = tuple(frac[i] * world.dims[i] for i in range(3))
     return cv.CameraPose.from_euler(pos, euler, far_clip=far_scale * world.max_dimension)
+
+
+def limited(cv, pose):
+    """The pose after UnityManager.LimitRotationHorizon (UnityManager.cs:193-201), as LateUpdate hands it to DrawWorld."""
+    import ctypes as C
+    from cpuvox_b200.native import lib
+    p = pose.to_native(16, 16)
+    lib.cvx_host_limit_rotation_horizon(C.byref(p))
+    return cv.CameraPose(tuple(p.position), tuple(p.rotation), pose.fov_y_degrees, pose.near_clip, pose.far_clip)
+
+
+def parse_obj(path):
+    """ObjModel.Import restated by the product's host code: triangle soup positions (n, 3) float32 and Color32 (n, 4) uint8."""
+    import ctypes as C
+    from cpuvox_b200.native import lib
+    pos, col, n = C.c_void_p(), C.c_void_p(), C.c_int32()
+    assert lib.cvx_obj_parse(path.encode(), 0, C.byref(pos), C.byref(col), C.byref(n)) == 0
+    try:
+        P = np.ctypeslib.as_array(C.cast(pos, C.POINTER(C.c_float)), (n.value, 3)).copy()
+        Cc = np.ctypeslib.as_array(C.cast(col, C.POINTER(C.c_uint8)), (n.value, 4)).copy()
+    finally:
+        lib.cvx_host_free(pos)
+        lib.cvx_host_free(col)
+    return P, Cc
 
 
 def setup_for(cv, world, spec, W, H):
