@@ -11,7 +11,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import COMB_POSES, MILL, POSES, ROOT, comb_world, crc, irregular_world, pose_for, setup_for
+from conftest import COMB_POSES, MILL, POSES, ROOT, comb_world, crc, irregular_world, limited, pose_for, setup_for
 from rle import encode_world
 
 pytestmark = pytest.mark.gpu
@@ -114,6 +114,77 @@ def test_matches_golden_fixtures(cv, rm, terrain_world, structure_world, mill_wo
             td, lr, cn, frame = _gpu_frame(rm, s, 0)
             assert cn == c["counters"], (name, c["pose"], W, H)
             assert (crc(td), crc(lr), crc(frame)) == (c["td_crc"], c["lr_crc"], c["frame_crc"]), (name, c["pose"], W, H)
+
+
+@pytest.mark.parametrize("world_name", ["terrain_world", "structure_world", "mill_world"])
+def test_matches_the_translated_reference(cv, ref, rm, request, world_name):
+    """CUDA raybuffers vs oracle/_ref — the reference's own DrawSegmentRayJob.cs / SegmentDDAData.cs / CameraData.cs /
+    World.cs / RenderManager.DrawSegments translated to C++ (oracle/ref.py) — tolerance 0; the frame against the reference's
+    BlitSegments + shader through the stand-in rasteriser within north_star's tolerance (>= 99.5 % identical pixels)."""
+    world = request.getfixturevalue(world_name)
+    rw = ref.RefWorld(world.dims, world.blobs, world.column_counts)
+    rm.upload_world(world)
+    rm.set_counters(False)
+    for (W, H) in RESOLUTIONS:
+        rm.set_resolution(W, H)
+        for spec in POSES:
+            s = setup_for(cv, world, spec, W, H)
+            rm.clear_raybuffers(0)
+            rm.draw_setup(s)
+            rm.sync()
+            td, lr = rm.read_raybuffers()
+            frame = rm.read_frame()
+            rtd, rlr = ref.render_raybuffers(rw, ref.copy_setup(s), W, H)
+            assert np.array_equal(td, rtd) and np.array_equal(lr, rlr), (world_name, spec[0], W, H)
+            rframe = ref.blit(ref.copy_setup(s), W, H, rtd, rlr)
+            assert (frame == rframe).mean() >= 0.995, (world_name, spec[0], W, H, (frame == rframe).mean())
+    rm.set_counters(True)
+
+
+def test_matches_golden_vectors_made_by_the_reference(cv, rm, terrain_world, structure_world, mill_world):
+    """tests/golden/golden_ref_v1.json: raybuffer CRCs produced by the translated reference's RenderManager.DrawWorld from the
+    recorded camera poses (tests/golden/make_golden_ref.py). No oracle, no reference library at run time."""
+    with open(os.path.join(ROOT, "tests", "golden", "golden_ref_v1.json")) as f:
+        golden = json.load(f)["worlds"]
+    worlds = {"terrain256": terrain_world, "structure512x128x256": structure_world, "mill256": mill_world}
+    rm.set_counters(False)
+    for name, g in golden.items():
+        w = worlds[name]
+        assert [crc(b) for b in w.blobs] == g["blob_crcs"], name
+        rm.upload_world(w)
+        for c in g["cases"]:
+            W, H = c["width"], c["height"]
+            rm.set_resolution(W, H)
+            pose = cv.CameraPose(tuple(c["position"]), tuple(c["rotation"]), far_clip=c["far_clip"])
+            s = cv.frame_setup(pose, W, H, np.array(c["lod_distances"], dtype=np.float32), w.dims[1], limit_horizon=False)
+            assert crc(np.frombuffer(bytes(s), dtype=np.uint8)) == c["setup_crc"], (name, c["pose"], W, H)
+            rm.clear_raybuffers(0)
+            rm.draw_setup(s)
+            rm.sync()
+            td, lr = rm.read_raybuffers()
+            assert (crc(td), crc(lr)) == (c["td_crc"], c["lr_crc"]), (name, c["pose"], W, H)
+    rm.set_counters(True)
+
+
+def test_mill_1024_matches_the_translated_reference_1080p(cv, ref, rm):
+    """BASELINE config 1 at full size against the reference's own code: mill 1024^3, 1920x1080, 6 poses of the benchmark path
+    (outside the world, looking up, the dive, the roll, the end pose)."""
+    world = cv.World.from_obj(MILL, 1024)
+    rw = ref.RefWorld(world.dims, world.blobs, world.column_counts)
+    rm.upload_world(world)
+    rm.set_counters(False)
+    W, H = 1920, 1080
+    rm.set_resolution(W, H)
+    poses = cv.benchmark_path(world.dims, 60, far_clip=2.0 * world.max_dimension)
+    for i in (0, 12, 24, 36, 48, 59):
+        s = rm.make_setup(poses[i])
+        rm.clear_raybuffers(0)
+        rm.draw_setup(s)
+        rm.sync()
+        td, lr = rm.read_raybuffers()
+        rtd, rlr = ref.render_raybuffers(rw, ref.copy_setup(s), W, H)
+        assert np.array_equal(td, rtd) and np.array_equal(lr, rlr), i
+    rm.set_counters(True)
 
 
 def test_counters_off_gives_identical_pixels(cv, rm, mill_world):
