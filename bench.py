@@ -131,30 +131,90 @@ def phase1_bytes(c):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def parse_obj_soup(path):
+    """ObjModel.Import (ObjModel.cs:10-167) for `v x y z [r g b]` / `f a b c` files: the triangle soup it builds (one vertex per
+    face corner, indices 0..n-1), colours through Unity's Color -> Color32 rounding. Pure Python: the CPU arm must not need the product."""
+    vs, cs, tri = [], [], []
+    with open(path) as f:
+        for line in f:
+            if line.startswith("v "):
+                q = line.split()
+                vs.append([float(q[1]), float(q[2]), float(q[3])])
+                cs.append([float(q[4]), float(q[5]), float(q[6])] if len(q) > 6 else [1.0, 1.0, 1.0])
+            elif line.startswith("f "):
+                tri.append([int(x.split("/")[0]) - 1 for x in line.split()[1:4]])
+    vs, cs, tri = np.array(vs, dtype=np.float32), np.array(cs, dtype=np.float32), np.array(tri).ravel()
+    col = np.rint(np.clip(cs, 0, 1) * np.float32(255)).astype(np.uint8)
+    col = np.concatenate([col, np.full((len(col), 1), 255, np.uint8)], 1)
+    return vs[tri], col[tri]
+
+
+class CpuPath:
+    """The reference's CPU implementation of the path, for `--impl reference` and the cpu_baseline leg. No product code:
+    kind "reference": oracle/_ref — the reference's own C# (voxelizer, RLE builder, DownSample, segment setup, DrawSegments + the four
+        jobs of DrawSegmentRayJob) translated to C++ and compiled (oracle/ref.py; no C# toolchain exists here), jobs spread over
+        all host threads with a shared batch counter like Unity's IJobParallelFor;
+    kind "port": oracle/cpuvox_oracle.cpp (hand restatement), only when the prebuilt oracle/_ref library is missing.
+    Phase 2 is a GPU shader in the reference (RayBufferBlit.shader); on the CPU arm it is the oracle's per-pixel restatement
+    (threaded), so that a CPU "frame" is the same product as a GPU frame. Camera path, LOD distances and LimitRotationHorizon
+    (UnityEngine / MonoBehaviour code) come from the oracle library's restatements."""
+
+    def __init__(self, maxdim, W, H, frames=FRAMES_PER_STEP):
+        from oracle import oracle as orc
+        from oracle import ref
+        self.orc, self.W, self.H = orc, W, H
+        self.kind = "reference" if ref.build() else "port"
+        self.threads = orc.hardware_threads()
+        P, C = parse_obj_soup(MILL)
+        if self.kind == "reference":
+            self.ref = ref
+            dims, blobs, ccs, _ = ref.build_world_from_mesh(P, C, np.arange(P.shape[0]), maxdim)   # flip X only: the UI default
+            self.world = ref.RefWorld(dims, blobs, ccs)
+            self.buffers = ref.alloc_raybuffers(W, H)
+        else:
+            import cpuvox_b200 as cv  # fallback only: the oracle has no world builder of its own
+            w = cv.World.from_obj(MILL, maxdim)
+            dims, blobs, ccs = w.dims, w.blobs, w.column_counts
+            self.buffers = (np.zeros((W + 2 * H, H), dtype=np.uint32), np.zeros((2 * W + H, W), dtype=np.uint32))
+        self.oworld = orc.OracleWorld(dims, blobs, ccs)
+        self.dims = dims
+        lods = orc.setup_lods(max(dims), W, H)
+        self.setups = []
+        for i in range(frames):
+            pos, rot = orc.benchmark_pose(1.15 * i / (frames - 1), dims)          # BenchmarkPath.anim, clip length 1.15
+            if self.kind == "reference":
+                rot = orc.limit_rotation_horizon(pos, rot)
+                self.setups.append(ref.frame_setup(pos, rot, W, H, lods, dims[1], far=2.0 * max(dims)))
+            else:
+                self.setups.append(orc.frame_setup(pos, rot, W, H, lods, dims[1], far=2.0 * max(dims)))
+        self.frame = np.zeros((H, W), dtype=np.uint32)
+
+    def render(self, i):
+        s = self.setups[i]
+        if self.kind == "reference":
+            td, lr = self.ref.render_raybuffers(self.world, s, self.W, self.H, threads=0, buffers=self.buffers)
+            s = self.orc.copy_setup(s)
+        else:
+            td, lr, _ = self.orc.render_raybuffers(self.oworld, s, self.W, self.H, threads=0, td=self.buffers[0], lr=self.buffers[1])
+        self.orc.blit(s, self.W, self.H, td, lr, threads=0, frame=self.frame)
+
+    def describe(self):
+        what = ("reference C# translated to C++ (oracle/_ref: cs2cpp.py, g++ -O2 -ffp-contract=off; not .NET, not Burst)" if self.kind == "reference"
+                else "hand C++ restatement (oracle/cpuvox_oracle.cpp)")
+        return f"Phase 1 = {what}, Phase 2 = per-pixel restatement of the blit shader; {self.threads} host threads"
+
+
 def run_reference(a, rank, world_size):
-    """--impl reference: the CPU restatement of the reference's own path on all host threads (the reference itself is C# on
-    Unity/Burst: not buildable here, so kind = "port"). Each step renders a bounded sample: 6 of the 60 poses."""
+    """--impl reference: the reference's own CPU implementation on all host threads, the same 60 poses per step as the repo arm."""
     if rank != 0:
         return
-    import cpuvox_b200 as cv  # host-side world production and frame setup only; nothing here touches a GPU
-    from oracle import oracle as orc
-
     W, H = [int(x) for x in a.res.split("x")]
-    world = cv.World.from_obj(MILL, a.maxdim)
-    ow = orc.OracleWorld(world.dims, world.blobs, world.column_counts)
-    lods = cv.setup_lods(world.max_dimension, W, H)
-    poses = cv.benchmark_path(world.dims, FRAMES_PER_STEP, far_clip=2.0 * world.max_dimension)
-    sample = list(range(0, FRAMES_PER_STEP, 10))
-    setups = [orc.copy_setup(cv.frame_setup(poses[i], W, H, lods, world.dims[1])) for i in sample]
-    td = np.zeros((W + 2 * H, H), dtype=np.uint32)
-    lr = np.zeros((2 * W + H, W), dtype=np.uint32)
-    frame = np.zeros((H, W), dtype=np.uint32)
-    threads = orc.hardware_threads()
+    cpu = CpuPath(a.maxdim, W, H)
+    n = len(cpu.setups)
 
     def step():
-        for s in setups:
-            orc.render_raybuffers(ow, s, W, H, threads=0, td=td, lr=lr)
-            orc.blit(s, W, H, td, lr, threads=0, frame=frame)
+        for i in range(n):
+            cpu.render(i)
 
     for _ in range(a.warmup):
         step()
@@ -162,14 +222,14 @@ def run_reference(a, rank, world_size):
     for _ in range(a.steps):
         step()
     dt = time.perf_counter() - t0
-    fps = len(setups) * a.steps / dt
-    sample_txt = f"poses {sample} of the {FRAMES_PER_STEP}-pose path per step, Phase 1 + Phase 2, {threads} threads"
+    fps = n * a.steps / dt
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1000.0 * dt / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "datasets/mill.obj (reference dataset), fixed camera path",
-        "config": {"workload": workload_name(a.maxdim, W, H), "resolution": [W, H], "frames_per_step": len(setups)},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample_txt},
+        "data": "datasets/mill.obj (reference dataset) voxelized in-process, fixed 60-pose camera path",
+        "config": {"workload": workload_name(a.maxdim, W, H), "resolution": [W, H], "frames_per_step": n},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cpu.threads, "kind": cpu.kind,
+                         "sample": f"all {n} poses of the path per step; " + cpu.describe()},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
@@ -372,26 +432,18 @@ def run_b200(a, rank, local_rank, world_size):
                             "runs_per_s": sum(c["runs_visited"] for c in r["per"]) / len(r["per"]) * fr / (r["ms"] / 1000.0)}
 
     if world_size == 1 and not a.no_cpu_baseline:
-        from oracle import oracle as orc  # cpu_baseline leg: the oracle as the timed CPU restatement, never on the product path
-        ow = orc.OracleWorld(world.dims, world.blobs, world.column_counts)
-        lods = cv.setup_lods(world.max_dimension, W, H)
-        osetups = [orc.copy_setup(cv.frame_setup(p, W, H, lods, world.dims[1])) for p in poses]
-        td = np.zeros((W + 2 * H, H), dtype=np.uint32)
-        lr = np.zeros((2 * W + H, W), dtype=np.uint32)
-        fr = np.zeros((H, W), dtype=np.uint32)
+        cpu = CpuPath(a.maxdim, W, H)   # the checker as the timed CPU arm (oracle/_ref), never on the product path
         t0 = time.perf_counter()
         done = 0
-        for _ in range(3):
-            for s in osetups:
-                orc.render_raybuffers(ow, s, W, H, threads=0, td=td, lr=lr)
-                orc.blit(s, W, H, td, lr, threads=0, frame=fr)
+        for _ in range(8):
+            for i in range(len(cpu.setups)):
+                cpu.render(i)
                 done += 1
             if time.perf_counter() - t0 > 12.0:
                 break
         dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": done / dt, "unit": "frames/s", "cores": orc.hardware_threads(), "kind": "port",
-                                "sample": f"{done} frames: the same {FRAMES_PER_STEP}-pose path at {W}x{H}, Phase 1 + Phase 2, all host threads; "
-                                          "C++ restatement of the reference (the C#/Burst original cannot be built here)"}
+        line["cpu_baseline"] = {"value": done / dt, "unit": "frames/s", "cores": cpu.threads, "kind": cpu.kind,
+                                "sample": f"{done} frames: whole passes over the same {FRAMES_PER_STEP}-pose path at {W}x{H}; " + cpu.describe()}
     print(json.dumps(line), flush=True)
     rm.destroy()
     if world_size > 1:

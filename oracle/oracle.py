@@ -126,6 +126,16 @@ def frame_setup(position, rotation, width, height, lod_distances, world_dim_y, f
     return out
 
 
+def limit_rotation_horizon(position, rotation):
+    """UnityManager.LimitRotationHorizon (UnityManager.cs:193-201): the rotation DrawWorld receives."""
+    p = Pose()
+    p.position[:] = position
+    p.rotation[:] = rotation
+    p.pixel_width = p.pixel_height = 16
+    lib().orc_limit_rotation_horizon(C.byref(p))
+    return tuple(p.rotation)
+
+
 def setup_lods(world_max_dimension, res_x, res_y, fov=85.0, lod_error=1.0) -> np.ndarray:
     out = (C.c_float * LODS)()
     lib().orc_setup_lods(world_max_dimension, res_x, res_y, fov, lod_error, C.byref(out))

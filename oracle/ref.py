@@ -162,10 +162,16 @@ def frame_setup(position, rotation, width, height, lod_distances, world_dim_y, f
     return out
 
 
-def render_raybuffers(world: RefWorld, setup: FrameSetup, width, height, threads=0):
+def alloc_raybuffers(width, height):
+    """Zeroed flat raybuffers padded to whole 256-ray partial textures (RayBuffer.cs:18-19), reusable across frames."""
     W, H = width, height
-    td = np.zeros((_pad_rows(W + 2 * H), H), dtype=np.uint32)
-    lr = np.zeros((_pad_rows(2 * W + H), W), dtype=np.uint32)
+    return np.zeros((_pad_rows(W + 2 * H), H), dtype=np.uint32), np.zeros((_pad_rows(2 * W + H), W), dtype=np.uint32)
+
+
+def render_raybuffers(world: RefWorld, setup: FrameSetup, width, height, threads=0, buffers=None):
+    W, H = width, height
+    td, lr = buffers if buffers is not None else alloc_raybuffers(W, H)
+    assert td.shape == (_pad_rows(W + 2 * H), H) and lr.shape == (_pad_rows(2 * W + H), W)
     _check(lib().ref_render_raybuffers(world._w, C.byref(setup), W, H, td.ctypes.data_as(C.c_void_p), lr.ctypes.data_as(C.c_void_p), threads),
            "ref_render_raybuffers")
     return td[:W + 2 * H], lr[:2 * W + H]
