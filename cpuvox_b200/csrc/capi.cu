@@ -100,12 +100,22 @@ int validate_setup(cvx_ctx* ctx, const cvx_frame_setup* s, int total) {
     if (tdRays > W + 2 * H || lrRays > 2 * W + H)
         return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "segment ray counts (%d top/down, %d left/right) exceed the raybuffers (%d, %d rows)", tdRays, lrRays, W + 2 * H, 2 * W + H);
     (void)total;
+    // RenderManager.cs:482-483 clamps RayCount at 0; a negative count would give a negative row offset (host_frame.h: ray_index_offset)
+    for (int k = 0; k < 4; k++)
+        if (s->segments[k].ray_count < 0) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "segment %d has a negative ray count (%d)", k, s->segments[k].ray_count);
     return CVX_OK;
 }
 
 void make_frame(cvx_ctx* ctx, const cvx_frame_setup* s, cvxd_frame& f) {
     cvxh::frame_from_setup(s, ctx->width, ctx->height, f);
     cvxd_frame_set_world(&f, &ctx->world);
+    // The reference indexes worldLODs / LODDistances unchecked (DrawSegmentRayJob.cs:123-128,237-243): a ray that passes
+    // LODDistances[lod] moves on to LOD lod + 1 whether or not it exists. Here the last uploaded LOD of the contiguous run from
+    // LOD 0 is never left: its distance and the ones after it are +inf (identical to the reference whenever the reference is
+    // well defined, i.e. every LOD a ray can reach exists and LODDistances[5] lies beyond the far clip, as SetupLods makes it).
+    int last = 0;
+    while (last + 1 < CVXD_LODS && ctx->world.lods[last + 1].headers) last++;
+    for (int i = last; i < CVXD_LODS; i++) f.lod_dist[i] = __builtin_inff();
     f.td = ctx->td; f.lr = ctx->lr;
     f.counters = (ctx->flags & CVX_FLAG_COUNTERS) ? ctx->counters : nullptr;
     f.general_path = ctx->generalPath;
@@ -202,7 +212,7 @@ int install_lod(cvx_ctx* ctx, int lod, int dim_x, int dim_y, int dim_z, void* db
     int r = cvxd_transcode_lod_device(ctx->stream, dblob, needCols, column_count, elementCells, lod, dim_y, &headers, &bounds, &regular, &bad, &ctx->launches, err);
     if (r) {
         cudaFree(dblob);
-        if (r == CVX_ERR_FORMAT) return fail(ctx, CVX_ERR_FORMAT, "column %lld of LOD %d points outside the element area", bad, lod);
+        if (r == CVX_ERR_FORMAT) return fail(ctx, CVX_ERR_FORMAT, "column %lld of LOD %d points outside the element area (element offset, run count or a run's colour range)", bad, lod);
         return fail(ctx, r, "world upload failed: %s", err.c_str());
     }
     cudaStreamSynchronize(ctx->stream);
@@ -454,21 +464,28 @@ int cvx_draw_batch(cvx_ctx* ctx, const cvx_frame_setup* setups, int32_t n_views,
     // inside the slot, and the K slots overlap each other — the long tail of one view's few heavy rays runs beside the bulk of
     // the next views, and frame copies run beside kernels. A caller-owned external frame forces one slot (one target buffer).
     const int K = ctx->externalFrame ? 1 : (ctx->slotCount < n_views ? ctx->slotCount : n_views);
+    for (int i = 0; i < n_views; i++)  // every view is checked before the first one is enqueued
+        if ((r = validate_setup(ctx, setups + i, 0))) return r;
     if ((r = ensure_slots(ctx, K))) return r;
     CU(ctx, cudaEventRecord(ctx->evBatchStart, ctx->stream)); // the slots start after everything queued on the context's stream
     for (int s = 1; s < K; s++) CU(ctx, cudaStreamWaitEvent(slot_stream(ctx, s), ctx->evBatchStart, 0));
-    for (int i = 0; i < n_views; i++) {
+    cudaError_t ce = cudaSuccess;
+    for (int i = 0; i < n_views && !r && ce == cudaSuccess; i++) {
         const int slot = i % K;
         uint32_t* target = ctx->externalFrame ? ctx->externalFrame : slot_frame(ctx, slot);
-        if ((r = draw_into(ctx, setups + i, slot, target, false))) return r;
+        r = draw_into(ctx, setups + i, slot, target, false);
         // the copy is asynchronous only if dst_frames is page-locked (cvx_alloc_pinned / cudaHostRegister)
-        if (dst_frames) CU(ctx, cudaMemcpyAsync((uint8_t*)dst_frames + (size_t)i * fbBytes, target, fbBytes, cudaMemcpyDeviceToHost, slot_stream(ctx, slot)));
+        if (!r && dst_frames) ce = cudaMemcpyAsync((uint8_t*)dst_frames + (size_t)i * fbBytes, target, fbBytes, cudaMemcpyDeviceToHost, slot_stream(ctx, slot));
     }
-    // join: whatever the caller queues next on the context's stream (events, reads, the next batch) comes after all views
+    // join — also after a failure in the middle of the batch, so that the slots' work stays ordered before whatever the caller
+    // queues next on the context's stream (events, reads, the next batch)
     for (int s = 1; s < K; s++) {
-        CU(ctx, cudaEventRecord(ctx->extra[s - 1].done, slot_stream(ctx, s)));
-        CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->extra[s - 1].done, 0));
+        cudaError_t e1 = cudaEventRecord(ctx->extra[s - 1].done, slot_stream(ctx, s));
+        if (e1 == cudaSuccess) e1 = cudaStreamWaitEvent(ctx->stream, ctx->extra[s - 1].done, 0);
+        if (ce == cudaSuccess) ce = e1;
     }
+    if (r) return r;
+    CU(ctx, ce);
     if (dst_frames) CU(ctx, cudaStreamSynchronize(ctx->stream)); // frames are on the host when the call returns
     return CVX_OK;
 }

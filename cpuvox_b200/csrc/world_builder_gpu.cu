@@ -314,7 +314,7 @@ int encode_lod(DeviceBuffers& mem, const unsigned long long* ukeys, const uint32
 
 // ---- device-side transcode of one LOD blob into the Phase-1 layout (same tables as world_transcode.h builds on the host) -----------
 // blob words: 3 per column header {elementOffset, runCount | worldMin << 16, worldMax | pad << 16}, then the element area.
-__global__ void transcode_count_kernel(const uint32_t* __restrict__ words, int64_t needCols, int64_t elementCells,
+__global__ void transcode_count_kernel(const uint32_t* __restrict__ words, int64_t needCols, int64_t columnCount, int64_t elementCells,
                                        unsigned long long* __restrict__ counts, long long* __restrict__ bad) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= needCols) return;
@@ -323,7 +323,19 @@ __global__ void transcode_count_kernel(const uint32_t* __restrict__ words, int64
     if (rc) {
         const int32_t off = (int32_t)w0;
         if (off < 0 || (int64_t)off + rc + 2 > elementCells) atomicMin(bad, (long long)i); // offsets + run counts must stay inside the element area
-        else n = rc + 1ull;
+        else {
+            n = rc + 1ull;
+            // the colour table follows the runs (World.cs:185-188): every solid run's ColorsIndex .. ColorsIndex + Length - 1 is gathered
+            // from it by Phase 1 (side colours, first/last colour of the caps), so it must stay inside the element area as well
+            const int64_t colourCells = elementCells - ((int64_t)off + rc + 2);
+            const uint32_t* el = words + 3 * columnCount + off + 1;
+            for (uint32_t k = 0; k < rc; k++) {
+                const uint32_t e = el[k];
+                const int ci = (int)(short)(e & 0xffffu), len = (int)(short)(e >> 16);
+                if (len == 0) break;                       // an invalid element ends the column (DrawSegmentRayJob.cs:445-447)
+                if (ci >= 0 && (len < 0 || (int64_t)ci + len > colourCells)) { atomicMin(bad, (long long)i); break; }
+            }
+        }
     }
     counts[i] = n;
 }
@@ -375,7 +387,7 @@ int cvxd_transcode_lod_device(cudaStream_t stream, const void* blob_dev, int64_t
     CK(cudaMemsetAsync(irregular, 0, 4, stream));
     CK(cudaMemsetAsync(counts + need_cols, 0, 8, stream));
     const unsigned blocks = (unsigned)((need_cols + 255) / 256);
-    transcode_count_kernel<<<blocks, 256, 0, stream>>>(words, need_cols, element_cells, counts, bad);
+    transcode_count_kernel<<<blocks, 256, 0, stream>>>(words, need_cols, column_count, element_cells, counts, bad);
     CK(cudaGetLastError());
     size_t tmpBytes = 0;
     CK(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, counts, offsets, (int)(need_cols + 1), stream));
@@ -385,7 +397,7 @@ int cvxd_transcode_lod_device(cudaStream_t stream, const void* blob_dev, int64_t
     CK(cudaMemcpyAsync(&hostBad, bad, 8, cudaMemcpyDeviceToHost, stream));
     CK(cudaMemcpyAsync(&total, offsets + need_cols, 8, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
-    if (hostBad != none) { *bad_column = hostBad; err = "column points outside the element area"; return CVX_ERR_FORMAT; }
+    if (hostBad != none) { *bad_column = hostBad; err = "column points outside the element area (element offset, run count or a run's colour range)"; return CVX_ERR_FORMAT; }
     void* headers = nullptr; void* bounds = nullptr;
     CK(cudaMalloc(&headers, (size_t)(16 * need_cols)));
     cudaError_t e = cudaMalloc(&bounds, total ? (size_t)total * 8 : 8);

@@ -52,6 +52,14 @@ inline bool cvxh_transcode_lod(const void* blob, int64_t need_cols, int64_t colu
         if (rc) {
             const int32_t off = (int32_t)w0;
             if (off < 0 || (int64_t)off + rc + 2 > element_cells) { out.bad_column = i; return false; }
+            // colour ranges of the solid runs (gathered by Phase 1) must stay inside the element area too
+            const int64_t colour_cells = element_cells - ((int64_t)off + rc + 2);
+            for (uint32_t k = 0; k < rc; k++) {
+                const uint32_t e = elements[(int64_t)off + 1 + k];
+                const int ci = (int)(int16_t)(e & 0xffffu), len = (int)(int16_t)(e >> 16);
+                if (len == 0) break;
+                if (ci >= 0 && (len < 0 || (int64_t)ci + len > colour_cells)) { out.bad_column = i; return false; }
+            }
             h.w = (uint32_t)out.bounds.size();
             int64_t y = dim_y;
             bool ok = true;

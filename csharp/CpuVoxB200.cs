@@ -86,8 +86,10 @@ public static unsafe class CpuVoxB200
 	{
 		for (int lod = 0; lod < worldLODs.Length; lod++) {
 			if (!worldLODs[lod].Exists) { continue; }
-			int3 d = worldLODs[lod].Dimensions;
-			Check(cvx_world_upload(ctx, lod, d.x << lod, d.y << lod, d.z << lod, // LOD-0 dimensions
+			// World.Dimensions is the LOD-0 size at EVERY LOD (World.DownSample: `new World(dimensions, lod + extraLods)`, World.cs:47;
+			// columns are indexed with `>> lod`, World.cs:145-149): pass it as is.
+			Unity.Mathematics.int3 d = worldLODs[lod].Dimensions;
+			Check(cvx_world_upload(ctx, lod, d.x, d.y, d.z,
 				worldLODs[lod].Storage.GetStartPointer(), worldLODs[lod].Storage.GetByteLength(), worldLODs[lod].ColumnCount), ctx);
 		}
 	}
@@ -102,9 +104,18 @@ public static unsafe class CpuVoxB200
 			dst[i] = *(Segment*)&sd; // same sequential layout
 		}
 		fixed (CameraData* cam = &camData) {
-			// CameraData = float4x4 + float2 + float + bool(4-byte marshalled) + float + fixed float[6]; copy field-wise if the
-			// managed bool is 1 byte in your build.
-			Buffer.MemoryCopy(cam, &s.Camera, sizeof(Camera), sizeof(Camera));
+			// CameraData (CameraData.cs:11-16) in memory: float4x4 WorldToScreenMatrix (private; 64 bytes, c0..c3) at 0, float2 PositionXZ
+			// at 64, float PositionY at 72, bool InverseElementIterationDirection at 76 (ONE byte + 3 bytes of padding whose content is
+			// undefined), float FarClip at 80, fixed float LODDistances[6] at 84. Copied field by field; the bool becomes an explicit
+			// 0 / 1 int. (Cleaner, if CameraData may be touched: add `public float4x4 WorldToScreen => WorldToScreenMatrix;`.)
+			float* f = (float*)cam;
+			for (int i = 0; i < 16; i++) { s.Camera.WorldToScreen[i] = f[i]; }
+			s.Camera.PositionX = camData.PositionXZ.x;
+			s.Camera.PositionZ = camData.PositionXZ.y;
+			s.Camera.PositionY = camData.PositionY;
+			s.Camera.InverseElementIterationDirection = camData.InverseElementIterationDirection ? 1 : 0;
+			s.Camera.FarClip = camData.FarClip;
+			for (int i = 0; i < LOD_LEVELS; i++) { s.Camera.LODDistances[i] = camData.LODDistances[i]; }
 		}
 		s.VanishingPointX = vanishingPointScreenSpace.x;
 		s.VanishingPointY = vanishingPointScreenSpace.y;

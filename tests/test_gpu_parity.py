@@ -454,16 +454,59 @@ def test_error_paths(cv):
         with pytest.raises(cv.CvxError) as e:
             m.upload_world(cv.World((8, 8, 8), [bad], [cc], [0]))
         assert e.value.code == -8  # CVX_ERR_FORMAT
+        # a run whose colour range (ColorsIndex + Length) leaves the element area: Phase 1 would gather out of bounds
+        g = np.zeros((8, 8, 8), dtype=np.uint32)
+        g[3, 2:5, 4] = 0x11223344
+        blob2, cc2 = encode_world(g)
+        words = blob2.copy().view(np.uint32)
+        hdr = words[:3 * cc2].reshape(cc2, 3)
+        col = 3 * 8 + 4
+        cells = words[3 * cc2:]
+        k = int(hdr[col, 0]) + 1
+        solid = next(i for i in range(k, k + int(hdr[col, 1] & 0xFFFF)) if (int(cells[i]) & 0xFFFF) < 0x8000)
+        cells[solid] = (int(cells[solid]) & 0xFFFF0000) | 0x7F00  # ColorsIndex 32512
+        with pytest.raises(cv.CvxError) as e:
+            m.upload_world(cv.World((8, 8, 8), [words.view(np.uint8)], [cc2], [3]))
+        assert e.value.code == -8  # CVX_ERR_FORMAT
         m.upload_world(cv.World((8, 8, 8), [blob], [cc], [0]))
         with pytest.raises(cv.CvxError) as e:
             m.draw_setup(s)
         assert e.value.code == -6  # CVX_ERR_NO_RESOLUTION
+        m.set_resolution(64, 48)
+        s.segments[0].ray_count = -3
+        s.segments[1].ray_count = 10
+        with pytest.raises(cv.CvxError) as e:
+            m.draw_setup(s)
+        assert e.value.code == -1  # CVX_ERR_INVALID_ARGUMENT: negative ray count
+        with pytest.raises(cv.CvxError):
+            m.draw_batch([N.FrameSetup(), s])  # refused before anything is enqueued
+        m.sync()
         with pytest.raises(cv.CvxError):
             m.set_resolution(0, 100)
         with pytest.raises(cv.CvxError):
             m.set_group_size(7)
     finally:
         m.destroy()
+
+
+def test_world_with_fewer_lods_than_distances(cv, orc, rm):
+    """A 3-LOD world drawn with SetupLods' six default distances and a far clip beyond all of them: the reference would index
+    LODs that do not exist (DrawSegmentRayJob.cs:237-243, unchecked); the library never leaves the last uploaded LOD, which equals
+    the oracle run with the distances of the missing LODs at infinity."""
+    world = cv.World.from_obj(MILL, 256, lods=3)
+    assert len(world.blobs) == 3
+    ow = orc.OracleWorld(world.dims, world.blobs, world.column_counts)
+    rm.upload_world(world)
+    W, H = 320, 180
+    rm.set_resolution(W, H)
+    lods = cv.setup_lods(world.max_dimension, W, H)
+    inf_lods = lods.copy()
+    inf_lods[2:] = np.inf
+    for spec in POSES[:6]:
+        pose = pose_for(cv, world, spec, far_scale=8.0)
+        s = cv.frame_setup(pose, W, H, lods, world.dims[1])
+        so = cv.frame_setup(pose, W, H, inf_lods, world.dims[1])
+        _assert_same(_gpu_frame(rm, s, 0), _oracle_frame(orc, ow, so, W, H, 0), f"3-LOD world {spec[0]}")
 
 
 @pytest.fixture(scope="module")
