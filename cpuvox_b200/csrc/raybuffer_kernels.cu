@@ -1011,48 +1011,228 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
 // The pixel takes the first segment with b >= 0 and c >= 0 (else the one with the largest min(b,c)); the ray row is
 // floor((offset_k + b/(b+c) * scale_k) * bufferRows) (shader :55-56, RenderManager.cs:235-242) clamped to the
 // segment's rows, the column is y (top/down) or x (left/right) (shader :58-62), point sampled.
-__global__ void __launch_bounds__(256)
-phase2_kernel(const __grid_constant__ cvxd_blit p) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int y = p.row_begin + blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= p.width || y >= p.row_end) return;
+//
+// phase2_kernel is a tile mover: one CTA per 64 x 32 screen tile, 8 pixels per thread.
+//  - Which segment a pixel belongs to is a sign test; almost every tile lies inside ONE segment (only the tiles the two diagonals
+//    through the vanishing point cross do not). Each warp decides that from the tile's four corner pixels with a safety margin
+//    (far above fp32 rounding), and then every pixel needs the two weights of that segment and ONE IEEE division, b / (b + c).
+//  - A warp instruction covers an 8 x 4 pixel block with the 8 along the raybuffer's contiguous axis (x for the left/right
+//    buffer, y for the top/down buffer): the ray row changes by about one row per pixel in both screen directions near the
+//    diagonals, so a 32 x 1 strip touches up to 32 rows (32 sectors) where the block touches ~12.
+//  - Top/down tiles are therefore read with lanes along y, staged in shared memory (pitch 36: conflict free both ways) and
+//    written to the frame with lanes along x (full 128-byte rows); left/right tiles are written directly.
+//  - Tiles crossed by a segment boundary take the general per-pixel path (every segment tested, as the restated formula reads).
+// Same arithmetic in all paths (IEEE fp32, no FMA contraction): the frame is bit-identical whichever path a pixel takes.
+struct P2Pixel { uint32_t color; bool owned; };
+
+// per-segment constants of the row formula (RenderManager.cs:235-242), computed once per thread
+struct P2Seg {
+    float e1x, e1y, e2x, e2y, det;  // VP -> MaxScreen (weight b), VP -> MinScreen (weight c), their cross product
+    float scale, offset, rowsF;     // _RayScale[k], _RayOffset[k], rows of the segment's raybuffer
+    int off01, rc, flatBase;        // first raybuffer row of the segment, its ray count, flat index of its first ray
+};
+__device__ __forceinline__ P2Seg p2_seg(const cvxd_blit& p, int k) {
+    P2Seg g;
+    g.e1x = p.seg[k].max_screen[0] - p.vp_x; g.e1y = p.seg[k].max_screen[1] - p.vp_y;
+    g.e2x = p.seg[k].min_screen[0] - p.vp_x; g.e2y = p.seg[k].min_screen[1] - p.vp_y;
+    g.det = g.e1x * g.e2y - g.e1y * g.e2x;
+    const int rows = k < 2 ? p.width + 2 * p.height : 2 * p.width + p.height;
+    g.rc = p.seg[k].ray_count;
+    g.rowsF = (float)rows;
+    g.scale = (float)g.rc / g.rowsF;
+    g.off01 = k == 1 ? p.seg[0].ray_count : (k == 3 ? p.seg[2].ray_count : 0);
+    g.offset = (k == 1 || k == 3) ? (float)g.off01 / g.rowsF : 0.0f;
+    g.flatBase = 0;
+    for (int j = 0; j < k; j++) g.flatBase += max(0, p.seg[j].ray_count);
+    return g;
+}
+
+// The shader's x = uv.x / (uv.x + uv.y) (RayBufferBlit.shader:55): uv.x, uv.y are the affine weights nb/det, nc/det of MaxScreen and
+// MinScreen; their common factor 1/det cancels, so the weights stay unnormalised (signs as for det > 0) and a pixel costs one division.
+// raybuffer row of a pixel with weights (nb, nc) in segment g, and whether this launch owns it (sharded mode)
+template <bool OWNED>
+__device__ __forceinline__ int p2_row(const cvxd_blit& p, const P2Seg& g, float nb, float nc, bool& owned) {
+    const float t = nb / (nb + nc);
+    const float v = g.offset + t * g.scale;
+    int row = f2i(floorf(v * g.rowsF));
+    row = max(g.off01, min(g.off01 + g.rc - 1, row));
+    owned = true;
+    if (OWNED) { const int flat = g.flatBase + row - g.off01; owned = flat >= p.ray_begin && flat < p.ray_end; }
+    return row;
+}
+template <bool OWNED>
+__device__ __forceinline__ P2Pixel p2_fetch(const cvxd_blit& p, const P2Seg& g, bool td, float nb, float nc, int x, int y) {
+    P2Pixel r; r.color = 0u;
+    const int row = p2_row<OWNED>(p, g, nb, nc, r.owned);
+    if (r.owned) r.color = td ? __ldg(p.td + (int64_t)row * p.height + y) : __ldg(p.lr + (int64_t)row * p.width + x);
+    return r;
+}
+
+// general path: the first active segment whose weights are both >= 0, else (rounding on an outer edge) the nearest one
+template <bool OWNED>
+__device__ __forceinline__ P2Pixel p2_pixel_general(const cvxd_blit& p, int x, int y) {
     const float px = (float)x + 0.5f, py = (float)y + 0.5f;
     const float dx = px - p.vp_x, dy = py - p.vp_y;
-    const int tdRows = p.width + 2 * p.height, lrRows = 2 * p.width + p.height;
     int best = -1; float bestB = 0.0f, bestC = 0.0f, bestScore = __int_as_float(0xff800000);
+    bool found = false;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        if (p.seg[k].ray_count <= 0 || (best >= 0 && bestB >= 0.0f && bestC >= 0.0f)) continue;
-        float e1x = p.seg[k].max_screen[0] - p.vp_x, e1y = p.seg[k].max_screen[1] - p.vp_y;
-        float e2x = p.seg[k].min_screen[0] - p.vp_x, e2y = p.seg[k].min_screen[1] - p.vp_y;
-        float det = e1x * e2y - e1y * e2x;
-        float b = (dx * e2y - dy * e2x) / det;
-        float c = (e1x * dy - e1y * dx) / det;
-        float score = minf_(b, c);
-        if (b >= 0.0f && c >= 0.0f) { best = k; bestB = b; bestC = c; }
-        else if (score > bestScore) { bestScore = score; best = k; bestB = b; bestC = c; }
-    }
-    uint32_t color = 0u;
-    bool owned = true;
-    if (best >= 0) {
-        const int rc = p.seg[best].ray_count;
-        const int rows = best < 2 ? tdRows : lrRows;
-        const float scale = (float)rc / (float)rows;
-        const int off01 = best == 1 ? p.seg[0].ray_count : (best == 3 ? p.seg[2].ray_count : 0);
-        const float offset = (best == 1 || best == 3) ? (float)off01 / (float)rows : 0.0f;
-        float t = bestB / (bestB + bestC);
-        float v = offset + t * scale;
-        int row = f2i(floorf(v * (float)rows));
-        row = max(off01, min(off01 + rc - 1, row));
-        if (p.owned_only) {
-            int flat = row - off01;
-            for (int k = 0; k < best; k++) flat += max(0, p.seg[k].ray_count);
-            owned = flat >= p.ray_begin && flat < p.ray_end;
+        if (p.seg[k].ray_count <= 0 || found) continue;
+        const float e1x = p.seg[k].max_screen[0] - p.vp_x, e1y = p.seg[k].max_screen[1] - p.vp_y;
+        const float e2x = p.seg[k].min_screen[0] - p.vp_x, e2y = p.seg[k].min_screen[1] - p.vp_y;
+        const float det = e1x * e2y - e1y * e2x;
+        float nb = dx * e2y - dy * e2x, nc = e1x * dy - e1y * dx;
+        if (det < 0.0f) { nb = -nb; nc = -nc; }
+        if (nb >= 0.0f && nc >= 0.0f) { best = k; bestB = nb; bestC = nc; found = true; }
+        else {
+            const float score = minf_(nb, nc) / fabsf(det);
+            if (score > bestScore) { bestScore = score; best = k; bestB = nb; bestC = nc; }
         }
-        if (owned) color = best < 2 ? __ldg(p.td + (int64_t)row * p.height + y) : __ldg(p.lr + (int64_t)row * p.width + x);
     }
-    if (owned) p.frame[(int64_t)y * p.width + x] = color;
+    if (best < 0) { P2Pixel r; r.color = 0u; r.owned = true; return r; }
+    const P2Seg g = p2_seg(p, best);
+    return p2_fetch<OWNED>(p, g, best < 2, bestB, bestC, x, y);
 }
+
+// a pixel known to lie inside segment g (both weights >= 0 there, and in no earlier segment): the same weights and row as above
+template <bool OWNED>
+__device__ __forceinline__ int p2_row_in(const cvxd_blit& p, const P2Seg& g, int x, int y, bool& owned) {
+    const float px = (float)x + 0.5f, py = (float)y + 0.5f;
+    const float dx = px - p.vp_x, dy = py - p.vp_y;
+    float nb = dx * g.e2y - dy * g.e2x, nc = g.e1x * dy - g.e1y * dx;
+    if (g.det < 0.0f) { nb = -nb; nc = -nc; }
+    return p2_row<OWNED>(p, g, nb, nc, owned);
+}
+
+#ifndef P2_TW /* tile width in pixels: 32 or 64 (8 pixels per thread); the height is 32 */
+#define P2_TW 64
+#endif
+#ifndef P2_MINB
+#define P2_MINB 6
+#endif
+#define P2_TH 32
+#define P2_PITCH (P2_TW + 4) /* = 4 mod 32: the staged top/down tile is bank-conflict free both ways */
+#ifndef CVX_EMU /* the emulator build covers Phase 1 only */
+template <bool OWNED>
+__global__ void __launch_bounds__(256, P2_MINB)
+phase2_kernel(const __grid_constant__ cvxd_blit p) {
+    constexpr int NX = P2_TW / 8;    // left/right path: 8-pixel groups along x per thread
+    constexpr int NH = P2_TW / 32;   // top/down path: 32-column halves of the tile
+    __shared__ uint32_t tile[P2_TH * P2_PITCH];
+    __shared__ uint32_t ownBits[P2_TH * NH];
+    __shared__ int uniShared;
+    __shared__ P2Seg segShared;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * P2_TW, y0 = p.row_begin + blockIdx.y * P2_TH;
+    const int xLast = min(x0 + P2_TW, p.width) - 1, yLast = min(y0 + P2_TH, p.row_end) - 1;
+
+    // ---- the segment that holds the whole tile, if one does: lanes 0..3 of warp 0 test one corner pixel each against every
+    // segment; the verdict and that segment's constants go to the other warps through shared memory
+    if (warp == 0) {
+        int u = -1;
+        const float px = (float)((lane & 1) ? xLast : x0) + 0.5f, py = (float)((lane & 2) ? yLast : y0) + 0.5f;
+        const float dx = px - p.vp_x, dy = py - p.vp_y;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            bool in = false;
+            if (p.seg[k].ray_count > 0) {
+                const float e1x = p.seg[k].max_screen[0] - p.vp_x, e1y = p.seg[k].max_screen[1] - p.vp_y;
+                const float e2x = p.seg[k].min_screen[0] - p.vp_x, e2y = p.seg[k].min_screen[1] - p.vp_y;
+                const float det = e1x * e2y - e1y * e2x;
+                const float tb0 = dx * e2y, tb1 = dy * e2x, tc0 = e1x * dy, tc1 = e1y * dx;
+                const float sgn = det > 0.0f ? 1.0f : -1.0f;
+                // margin: 1e-5 of the products' magnitude, ~40x the rounding error of the difference; a linear function that
+                // clears it at the four corners is positive — also as computed — at every pixel of the tile
+                const float nb = (tb0 - tb1) * sgn, nc = (tc0 - tc1) * sgn;
+                in = fabsf(det) > 1e-20f && fabsf(det) < 1e30f && nb > 1e-5f * (fabsf(tb0) + fabsf(tb1)) && nc > 1e-5f * (fabsf(tc0) + fabsf(tc1));
+            }
+            const uint32_t m = __ballot_sync(FULL_MASK, in) & 0xfu;
+            if (u < 0 && m == 0xfu) u = k;
+        }
+        if (lane == 0) {
+            uniShared = u;
+            if (u >= 0) segShared = p2_seg(p, u);
+        }
+    }
+    if (OWNED && threadIdx.x < P2_TH * NH) ownBits[threadIdx.x] = 0u;
+    __syncthreads();
+    const int uni = uniShared;
+
+    if (uni >= 2) {
+        // ---- left/right segment: lanes 8 along x, 4 along y; read and write directly. The rows first, then the gathers back
+        // to back, then the stores (pixels beyond the screen edge: clamped, not stored)
+        const P2Seg g = segShared;
+        const int y = y0 + (lane >> 3) + 4 * warp;
+        int xs[NX]; const uint32_t* src[NX]; bool ok[NX]; uint32_t col[NX];
+        const int yc = min(y, yLast);
+#pragma unroll
+        for (int j = 0; j < NX; j++) {
+            const int x = x0 + (lane & 7) + 8 * j;
+            xs[j] = min(x, xLast);
+            bool owned;
+            const int row = p2_row_in<OWNED>(p, g, xs[j], yc, owned);
+            ok[j] = owned && x <= xLast && y <= yLast;
+            src[j] = p.lr + (int64_t)row * p.width + xs[j];
+        }
+#pragma unroll
+        for (int j = 0; j < NX; j++) col[j] = (!OWNED || ok[j]) ? __ldg(src[j]) : 0u;
+#pragma unroll
+        for (int j = 0; j < NX; j++) if (ok[j]) p.frame[(int64_t)y * p.width + xs[j]] = col[j];
+        return;
+    }
+    if (uni >= 0) {
+        // ---- top/down segment: lanes 8 along y (the raybuffer's contiguous axis), 4 along x; staged for the row-major write
+        const P2Seg g = segShared;
+        const uint32_t* src[4 * NH]; bool ok[4 * NH]; uint32_t col[4 * NH];
+#pragma unroll
+        for (int h = 0; h < NH; h++) {
+            const int x = x0 + (lane >> 3) + 4 * warp + 32 * h, xc = min(x, xLast);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int y = y0 + (lane & 7) + 8 * j, yc = min(y, yLast);
+                bool owned;
+                const int row = p2_row_in<OWNED>(p, g, xc, yc, owned);
+                ok[h * 4 + j] = owned && x <= xLast && y <= yLast;
+                src[h * 4 + j] = p.td + (int64_t)row * p.height + yc;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4 * NH; i++) col[i] = (!OWNED || ok[i]) ? __ldg(src[i]) : 0u;
+#pragma unroll
+        for (int h = 0; h < NH; h++) {
+            const int lx = (lane >> 3) + 4 * warp + 32 * h;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int ly = (lane & 7) + 8 * j;
+                tile[ly * P2_PITCH + lx] = col[h * 4 + j];
+                if (OWNED && ok[h * 4 + j]) atomicOr(&ownBits[ly * NH + h], 1u << (lx & 31));
+            }
+        }
+    } else {
+        // ---- a segment boundary crosses the tile (or no segment is active): general per-pixel path, lanes along x
+#pragma unroll
+        for (int h = 0; h < NH; h++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int ly = warp + 8 * j, x = x0 + lane + 32 * h, y = y0 + ly;
+                if (x <= xLast && y <= yLast) {
+                    const P2Pixel r = p2_pixel_general<OWNED>(p, x, y);
+                    if (r.owned) p.frame[(int64_t)y * p.width + x] = r.color;
+                }
+            }
+        return;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < NH; h++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int ly = warp + 8 * j, x = x0 + lane + 32 * h, y = y0 + ly;
+            if (x <= xLast && y <= yLast && (!OWNED || ((ownBits[ly * NH + h] >> lane) & 1u))) p.frame[(int64_t)y * p.width + x] = tile[ly * P2_PITCH + lane + 32 * h];
+        }
+}
+
+#endif /* !CVX_EMU */
 
 // ---- debug views: the shader's COPY_MAIN1 / COPY_MAIN2 variants (RayBufferBlit.shader:48-53) -----------------------
 // uv = SV_POSITION.xy / _ScreenParams.xy with the pixel centre measured from the TOP (D3D); the fragment
@@ -1152,8 +1332,9 @@ cudaError_t cvxd_launch_phase1(const cvxd_world& world, const cvxd_frame& frame,
 cudaError_t cvxd_launch_phase2(const cvxd_blit& blit, cudaStream_t stream) {
     int rows = blit.row_end - blit.row_begin;
     if (rows <= 0 || blit.width <= 0) return cudaSuccess;
-    dim3 grid((blit.width + 31) / 32, (rows + 7) / 8);
-    phase2_kernel<<<grid, 256, 0, stream>>>(blit);
+    dim3 grid((blit.width + P2_TW - 1) / P2_TW, (rows + P2_TH - 1) / P2_TH);
+    if (blit.owned_only) phase2_kernel<true><<<grid, 256, 0, stream>>>(blit);
+    else phase2_kernel<false><<<grid, 256, 0, stream>>>(blit);
     return cudaGetLastError();
 }
 

@@ -1185,11 +1185,13 @@ int orc_blit(const orc_frame_setup* s, int32_t W, int32_t H, const uint32_t* td,
                 float e2x = sg.min_screen[0] - vx, e2y = sg.min_screen[1] - vy; // VP -> Min (weight c)
                 float dx = px - vx, dy = py - vy;
                 float det = e1x * e2y - e1y * e2x;
-                float b = (dx * e2y - dy * e2x) / det;
-                float c = (e1x * dy - e1y * dx) / det;
-                float score = m_min(b, c);
-                if (b >= 0.0f && c >= 0.0f) { best = k; bestB = b; bestC = c; break; }
-                if (score > bestScore) { bestScore = score; best = k; bestB = b; bestC = c; }
+                // The interpolated uv.x, uv.y of the shader are the affine weights nb/det, nc/det; x = uv.x / (uv.x + uv.y) (shader :55)
+                // does not depend on the common factor 1/det, so the weights are kept unnormalised (signs as for det > 0).
+                float nb = dx * e2y - dy * e2x, nc = e1x * dy - e1y * dx;
+                if (det < 0.0f) { nb = -nb; nc = -nc; }
+                if (nb >= 0.0f && nc >= 0.0f) { best = k; bestB = nb; bestC = nc; break; }
+                float score = m_min(nb, nc) / fabsf(det);  // outside every triangle (rounding on an outer edge): the nearest one
+                if (score > bestScore) { bestScore = score; best = k; bestB = nb; bestC = nc; }
             }
             uint32_t color = 0;
             if (best >= 0) {

@@ -529,7 +529,7 @@ def execute_ray(worlds, seg, ray, lod, row, m, pos_y, far_clip, lod_dist, ITER, 
 def blit(setup, W, H, td, lr):
     """BlitSegments + RayBufferBlit.shader frag (RenderManager.cs:199-256, Shaders/RayBufferBlit.shader:55-62), vectorised over the
     screen: pixel centres (x + 0.5, y + 0.5), bottom-left origin; triangle k = (VP, MaxScreen_k, MinScreen_k) carries uv (0,0), (1,0),
-    (0,1), so uv.x / uv.y are the affine weights b, c of Max / Min; x = b / (b + c); row = floor((offset_k + x * scale_k) * rows)
+    (0,1), so uv.x / uv.y are the affine weights b, c of Max / Min (kept unnormalised: times |det|); x = b / (b + c); row = floor((offset_k + x * scale_k) * rows)
     clamped to the segment's rows; column = y (top/down) or x (left/right). A pixel takes the first segment with b, c >= 0, else the
     one with the largest min(b, c) (the GPU rasteriser's coverage rule at shared edges is not reproducible)."""
     vx, vy = F(setup.vanishing_point_screen[0]), F(setup.vanishing_point_screen[1])
@@ -550,10 +550,13 @@ def blit(setup, W, H, td, lr):
             e1x, e1y = F(sg.max_screen[0]) - vx, F(sg.max_screen[1]) - vy
             e2x, e2y = F(sg.min_screen[0]) - vx, F(sg.min_screen[1]) - vy
             det = e1x * e2y - e1y * e2x
-            b = (dx * e2y - dy * e2x) / det
-            c = (e1x * dy - e1y * dx) / det
+            # unnormalised affine weights (x = uv.x / (uv.x + uv.y) does not depend on the common factor 1/det)
+            b = dx * e2y - dy * e2x
+            c = e1x * dy - e1y * dx
+            if det < 0:
+                b, c = -b, -c
             inside = (b >= 0) & (c >= 0) & ~done
-            sc = np.minimum(b, c)
+            sc = np.minimum(b, c) / np.abs(det)
             better = ~done & ~inside & (sc > score)
             take = inside | better
             best[take] = k
