@@ -26,6 +26,8 @@ static_assert(CVX_LOD_LEVELS == CVXD_LODS, "lod levels");
 #define CVX_MAX_SLOTS 8
 #define CVX_DEFAULT_SLOTS 6
 
+extern "C" int cvx_ring_close(cvx_ctx* ctx);
+
 struct cvx_slot {
     cudaStream_t stream = nullptr;
     uint32_t* td = nullptr;
@@ -66,6 +68,12 @@ struct cvx_ctx {
     int64_t launches = 0;
     std::vector<cudaEvent_t> profEvents; // 3 per profiled view: start, mid, end
     int profCapacity = 0, profCount = 0;
+    // frame ring (multi-GPU, rays sharded): `ringSlots` framebuffers + flag words in one allocation that lives on the root rank;
+    // the other ranks hold an IPC mapping of it. Flag words: arrive[slot][rank] and released[slot] (see cvx_ring_create).
+    uint8_t* ring = nullptr;
+    bool ringOwner = false;
+    int ringSlots = 0, ringWorld = 0;
+    size_t ringFrameBytes = 0;
     int groupSize = 0;                  // lanes per ray in phase 1: 0 = auto, 8, 16, 32
     int generalPath = 0;                // 1 = never use the boundary-table kernel
     std::string error;
@@ -146,6 +154,42 @@ uint32_t* slot_lr(cvx_ctx* ctx, int s) { return s == 0 ? ctx->lr : ctx->extra[s 
 uint32_t* slot_frame(cvx_ctx* ctx, int s) { return s == 0 ? ctx->frames[0] : ctx->extra[s - 1].frame; }
 
 uint32_t* current_target(cvx_ctx* ctx) { return ctx->externalFrame ? ctx->externalFrame : slot_frame(ctx, ctx->lastSlot); }
+
+// ---- frame ring: device-side flow control between ranks (no host barrier, no collective on the data path) ------------------
+#define CVX_RING_MAX_RANKS 64
+#define CVX_RING_TIMEOUT_NS 4000000000ll /* a peer that never signals must not hang the GPU: give up after 4 s and flag an error */
+struct ring_flags {
+    uint32_t arrive[CVX_RING_MAX_RANKS];  // arrive[r] = view index + 1 of the last view rank r finished storing into this slot
+    uint32_t released;                    // view index + 1 of the last view the root has consumed from this slot
+    uint32_t error;                       // set by a wait that timed out
+    uint32_t pad[62];
+};
+__device__ __forceinline__ uint32_t ring_load(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// thread i waits until flags[i] >= value
+__global__ void ring_wait_kernel(const uint32_t* flags, int n, uint32_t value, uint32_t* error) {
+    const int i = threadIdx.x;
+    if (i >= n) return;
+    long long t0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    while ((int32_t)(ring_load(flags + i) - value) < 0) {
+        __nanosleep(256);
+        long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        if (t - t0 > CVX_RING_TIMEOUT_NS) { atomicExch(error, 1u); break; }
+    }
+    __threadfence_system();
+}
+// everything this stream stored before (this rank's pixels of the view, through the peer mapping) is visible before the flag
+__global__ void ring_signal_kernel(uint32_t* flag, uint32_t value) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flag), "r"(value) : "memory");
+}
+uint32_t* ring_frame(cvx_ctx* ctx, int slot) { return (uint32_t*)(ctx->ring + (size_t)slot * ctx->ringFrameBytes); }
+ring_flags* ring_flag_block(cvx_ctx* ctx, int slot) { return (ring_flags*)(ctx->ring + (size_t)ctx->ringSlots * ctx->ringFrameBytes) + slot; }
 
 void free_extra_slots(cvx_ctx* ctx) {
     for (int i = 0; i < CVX_MAX_SLOTS - 1; i++) {
@@ -278,6 +322,7 @@ int cvx_destroy(cvx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copyStream) cudaStreamSynchronize(ctx->copyStream);
+    cvx_ring_close(ctx);
     free_resolution(ctx);
     free_world(ctx);
     for (cudaEvent_t e : ctx->profEvents) cudaEventDestroy(e);
@@ -348,6 +393,7 @@ int cvx_set_resolution(cvx_ctx* ctx, int32_t width, int32_t height) {
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->copyStream));
+    cvx_ring_close(ctx);  // its frames have the old size
     free_resolution(ctx);
     const size_t tdBytes = (size_t)height * (size_t)(width + 2 * height) * 4; // RenderManager.cs:36
     const size_t lrBytes = (size_t)width * (size_t)(2 * width + height) * 4;  // RenderManager.cs:35
@@ -515,6 +561,8 @@ int cvx_sync(cvx_ctx* ctx) {
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->copyStream));
+    if (ctx->ring)  // sharded views run on the slot streams without a join into the context's stream
+        for (int i = 0; i < CVX_MAX_SLOTS - 1; i++) if (ctx->extra[i].stream) CU(ctx, cudaStreamSynchronize(ctx->extra[i].stream));
     return CVX_OK;
 }
 
@@ -827,6 +875,126 @@ int cvx_ipc_close(cvx_ctx* ctx, void* device_ptr) {
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaIpcCloseMemHandle(device_ptr));
     return CVX_OK;
+}
+
+// ---- frame ring -----------------------------------------------------------------------------------------------------------------
+static size_t ring_bytes(size_t frameBytes, int slots) { return (size_t)slots * frameBytes + (size_t)slots * sizeof(ring_flags); }
+
+int cvx_ring_close(cvx_ctx* ctx) {
+    if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
+    if (!ctx->ring) return CVX_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copyStream);
+    for (int i = 0; i < CVX_MAX_SLOTS - 1; i++) if (ctx->extra[i].stream) cudaStreamSynchronize(ctx->extra[i].stream);
+    if (ctx->ringOwner) cudaFree(ctx->ring); else cudaIpcCloseMemHandle(ctx->ring);
+    ctx->ring = nullptr; ctx->ringSlots = 0; ctx->ringWorld = 0; ctx->ringOwner = false;
+    return CVX_OK;
+}
+
+int cvx_ring_create(cvx_ctx* ctx, int32_t slots, int32_t world_size, uint8_t out_handle[CVX_IPC_HANDLE_BYTES]) {
+    if (!ctx || !out_handle) return CVX_ERR_INVALID_ARGUMENT;
+    if (ctx->width <= 0) return fail(ctx, CVX_ERR_NO_RESOLUTION, "no resolution set");
+    if (slots < 1 || slots > 64 || world_size < 1 || world_size > CVX_RING_MAX_RANKS) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "ring of %d slots for %d ranks", slots, world_size);
+    cvx_ring_close(ctx);
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t fb = (size_t)ctx->width * ctx->height * 4;
+    void* mem = nullptr;
+    CU(ctx, cudaMalloc(&mem, ring_bytes(fb, slots)));
+    cudaError_t e = cudaMemsetAsync(mem, 0, ring_bytes(fb, slots), ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, mem);
+    if (e != cudaSuccess) { cudaFree(mem); return fail(ctx, CVX_ERR_CUDA, "frame ring: %s", cudaGetErrorString(e)); }
+    memcpy(out_handle, &h, sizeof h);
+    ctx->ring = (uint8_t*)mem; ctx->ringOwner = true; ctx->ringSlots = slots; ctx->ringWorld = world_size; ctx->ringFrameBytes = fb;
+    return CVX_OK;
+}
+
+int cvx_ring_open(cvx_ctx* ctx, const uint8_t handle[CVX_IPC_HANDLE_BYTES], int32_t slots, int32_t world_size) {
+    if (!ctx || !handle) return CVX_ERR_INVALID_ARGUMENT;
+    if (ctx->width <= 0) return fail(ctx, CVX_ERR_NO_RESOLUTION, "no resolution set");
+    if (slots < 1 || slots > 64 || world_size < 1 || world_size > CVX_RING_MAX_RANKS) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "ring of %d slots for %d ranks", slots, world_size);
+    cvx_ring_close(ctx);
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void* mem = nullptr;
+    CU(ctx, cudaIpcOpenMemHandle(&mem, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->ring = (uint8_t*)mem; ctx->ringOwner = false; ctx->ringSlots = slots; ctx->ringWorld = world_size;
+    ctx->ringFrameBytes = (size_t)ctx->width * ctx->height * 4;
+    return CVX_OK;
+}
+
+// One rank's share of view `view_index`: waits (on the device) until the root has released the ring slot, runs Phase 1 for the rays
+// [ray_begin, ray_end), Phase 2 for the pixels those rays feed — stored straight into the ring frame on the root (NVLink peer stores
+// when this is not the root) — and signals arrive[slot][rank]. Views rotate over the context's frame slots like cvx_draw_batch.
+int cvx_draw_sharded(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t ray_begin, int32_t ray_end, int64_t view_index, int32_t rank) {
+    int r = check_ready(ctx, setup);
+    if (r) return r;
+    if (!ctx->ring) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "no frame ring (cvx_ring_create / cvx_ring_open)");
+    if (rank < 0 || rank >= ctx->ringWorld || view_index < 0) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "rank %d / view %lld outside the ring", rank, (long long)view_index);
+    if ((r = validate_setup(ctx, setup, 0))) return r;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int K = ctx->slotCount;
+    if ((r = ensure_slots(ctx, K))) return r;
+    const int slot = (int)(view_index % K), rslot = (int)(view_index % ctx->ringSlots);
+    cudaStream_t stream = slot_stream(ctx, slot);
+    cvxd_frame f;
+    make_frame(ctx, setup, f);
+    f.td = slot_td(ctx, slot); f.lr = slot_lr(ctx, slot);
+    if (ray_end < 0 || ray_end > f.total_rays) ray_end = f.total_rays;
+    if (ray_begin < 0) ray_begin = 0;
+    f.ray_begin = ray_begin; f.ray_end = ray_end;
+    ring_flags* fl = ring_flag_block(ctx, rslot);
+    if (view_index >= ctx->ringSlots) {  // the slot still holds view_index - slots until the root releases it
+        ring_wait_kernel<<<1, 32, 0, stream>>>(&fl->released, 1, (uint32_t)(view_index - ctx->ringSlots + 1), &fl->error);
+        ctx->launches++;
+    }
+    CU(ctx, cvxd_launch_phase1(ctx->world, f, ctx->groupSize, stream));
+    if (ray_end > ray_begin) ctx->launches++;
+    cvxd_blit b;
+    make_blit(ctx, f, ring_frame(ctx, rslot), b);
+    b.td = f.td; b.lr = f.lr;
+    b.ray_begin = ray_begin; b.ray_end = ray_end; b.owned_only = 1;
+    CU(ctx, cvxd_launch_phase2(b, stream));
+    ring_signal_kernel<<<1, 1, 0, stream>>>(&fl->arrive[rank], (uint32_t)(view_index + 1));
+    ctx->launches += 2;
+    CU(ctx, cudaGetLastError());
+    ctx->lastSlot = slot;
+    return CVX_OK;
+}
+
+// Root only: waits (device side, on the copy stream) until every rank has stored its pixels of `view_index`, copies the frame to
+// dst_host if given (pinned memory for an asynchronous copy), and releases the ring slot for view_index + slots.
+// out_device_frame (optional) receives the frame's device address (valid until the slot is reused).
+int cvx_ring_consume(cvx_ctx* ctx, int64_t view_index, void* dst_host, void** out_device_frame) {
+    if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
+    if (!ctx->ring || !ctx->ringOwner) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "cvx_ring_consume is for the rank that created the ring");
+    if (view_index < 0) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "view index < 0");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int rslot = (int)(view_index % ctx->ringSlots);
+    ring_flags* fl = ring_flag_block(ctx, rslot);
+    ring_wait_kernel<<<1, CVX_RING_MAX_RANKS, 0, ctx->copyStream>>>(fl->arrive, ctx->ringWorld, (uint32_t)(view_index + 1), &fl->error);
+    if (dst_host) CU(ctx, cudaMemcpyAsync(dst_host, ring_frame(ctx, rslot), ctx->ringFrameBytes, cudaMemcpyDeviceToHost, ctx->copyStream));
+    ring_signal_kernel<<<1, 1, 0, ctx->copyStream>>>(&fl->released, (uint32_t)(view_index + 1));
+    ctx->launches += 2;
+    CU(ctx, cudaGetLastError());
+    if (out_device_frame) *out_device_frame = ring_frame(ctx, rslot);
+    return CVX_OK;
+}
+
+// 0 = no wait of this context's ring has timed out so far (call after cvx_sync; root only sees every slot's flag block)
+int cvx_ring_status(cvx_ctx* ctx) {
+    if (!ctx || !ctx->ring) return CVX_ERR_INVALID_ARGUMENT;
+    CU(ctx, cudaSetDevice(ctx->device));
+    int bad = 0;
+    for (int s = 0; s < ctx->ringSlots; s++) {
+        uint32_t e = 0;
+        CU(ctx, cudaMemcpy(&e, &ring_flag_block(ctx, s)->error, 4, cudaMemcpyDeviceToHost));
+        bad |= e != 0;
+    }
+    return bad ? fail(ctx, CVX_ERR_CUDA, "a frame-ring wait timed out (a rank did not deliver its share of a view)") : CVX_OK;
 }
 
 int cvx_alloc_pinned(int64_t bytes, void** out) {

@@ -410,6 +410,30 @@ class RenderManager:
     def ipc_close(self, device_ptr: int):
         self._ck(lib.cvx_ipc_close(self._ctx, C.c_void_p(device_ptr)))
 
+    # -- frame ring: pipelined gather of ray-sharded views (cvx_ring_*) ----------------------------------------------
+    def ring_create(self, slots: int, world_size: int) -> bytes:
+        h = (C.c_uint8 * 64)()
+        self._ck(lib.cvx_ring_create(self._ctx, slots, world_size, C.byref(h)))
+        return bytes(h)
+
+    def ring_open(self, handle: bytes, slots: int, world_size: int):
+        h = (C.c_uint8 * 64)(*handle)
+        self._ck(lib.cvx_ring_open(self._ctx, C.byref(h), slots, world_size))
+
+    def ring_close(self):
+        self._ck(lib.cvx_ring_close(self._ctx))
+
+    def draw_sharded(self, setup: FrameSetup, ray_begin: int, ray_end: int, view_index: int, rank: int):
+        self._ck(lib.cvx_draw_sharded(self._ctx, C.byref(setup), ray_begin, ray_end, view_index, rank))
+
+    def ring_consume(self, view_index: int, dst: Optional[np.ndarray] = None) -> int:
+        p = C.c_void_p()
+        self._ck(lib.cvx_ring_consume(self._ctx, view_index, _ptr(dst) if dst is not None else None, C.byref(p)))
+        return p.value
+
+    def ring_status(self):
+        self._ck(lib.cvx_ring_status(self._ctx))
+
     def set_external_frame(self, device_ptr: int):
         self._ck(lib.cvx_set_external_frame(self._ctx, C.c_void_p(device_ptr)))
 

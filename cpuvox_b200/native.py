@@ -142,6 +142,12 @@ SYMBOLS = {
     "cvx_ipc_export_frame": (C.c_int, [_P, C.POINTER(C.c_uint8 * 64)]),
     "cvx_ipc_open": (C.c_int, [_P, C.POINTER(C.c_uint8 * 64), C.POINTER(_P)]),
     "cvx_ipc_close": (C.c_int, [_P, _P]),
+    "cvx_ring_create": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_uint8 * 64)]),
+    "cvx_ring_open": (C.c_int, [_P, C.POINTER(C.c_uint8 * 64), C.c_int32, C.c_int32]),
+    "cvx_ring_close": (C.c_int, [_P]),
+    "cvx_draw_sharded": (C.c_int, [_P, C.POINTER(FrameSetup), C.c_int32, C.c_int32, C.c_int64, C.c_int32]),
+    "cvx_ring_consume": (C.c_int, [_P, C.c_int64, _P, C.POINTER(_P)]),
+    "cvx_ring_status": (C.c_int, [_P]),
     "cvx_debug_ray_setup": (C.c_int, [_P, C.POINTER(FrameSetup), C.POINTER(RayState), _I32]),
     "cvx_debug_ray_timing": (C.c_int, [_P, C.POINTER(FrameSetup), _P, _I32]),
     "cvx_host_quat_euler": (None, [_F, _F, _F, C.POINTER(_F * 4)]),

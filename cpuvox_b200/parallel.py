@@ -92,16 +92,24 @@ def broadcast_world(world: Optional[World], src: int = 0, device=None, group=Non
 
 
 class ShardedRenderManager:
-    """One rank's share of a multi-GPU render. Wraps a RenderManager on `device`."""
+    """One rank's share of a multi-GPU render. Wraps a RenderManager on `device`.
 
-    def __init__(self, device: int, rank: int, world_size: int, gather: str = "p2p", group=None):
-        if gather not in ("p2p", "reduce"):
-            raise ValueError("gather must be 'p2p' or 'reduce'")
+    gather: "p2p"    one view at a time: peer stores into the root's framebuffer, a host barrier per view;
+            "ring"   a stream of views: peer stores into a ring of framebuffers on the root, all ordering between ranks on the
+                     device (flag words polled by tiny kernels), no host barrier and no collective between views;
+            "reduce" fallback: zero-initialised disjoint framebuffers summed with ncclReduce."""
+
+    def __init__(self, device: int, rank: int, world_size: int, gather: str = "p2p", group=None, ring_slots: int = 4):
+        if gather not in ("p2p", "reduce", "ring"):
+            raise ValueError("gather must be 'p2p', 'ring' or 'reduce'")
         self.rm = RenderManager(device)
         self.device, self.rank, self.world_size, self.gather, self.group = device, rank, world_size, gather, group
+        self.ring_slots = ring_slots
         self._root_frame_ptr = 0      # mapped pointer to rank 0's framebuffer (p2p, rank != 0)
         self._frame_tensor = None     # torch int32 tensor aliasing this rank's framebuffer (reduce)
         self._stream = None
+        self._next_view = 0           # ring: running view index, the same on every rank
+        self._ring_ready = False
 
     def upload_world(self, world: World):
         self.rm.upload_world(world)
@@ -110,18 +118,33 @@ class ShardedRenderManager:
         import torch
         import torch.distributed as dist
 
-        if not self.rm.set_resolution(width, height) and (self._root_frame_ptr or self._frame_tensor is not None or self.world_size == 1):
+        same = width == self.rm.width and height == self.rm.height
+        if same and (self._root_frame_ptr or self._frame_tensor is not None or self._ring_ready or self.world_size == 1):
             return
-        if self.world_size == 1:
-            return
-        if self.gather == "p2p":
+        if self.world_size > 1 and not same:
+            # peers close their mappings of the root's memory BEFORE the root reallocates it (CUDA IPC rule), then everyone moves on
             if self._root_frame_ptr:
                 self.rm.ipc_close(self._root_frame_ptr)
                 self._root_frame_ptr = 0
+            if self._ring_ready and self.rank != 0:
+                self.rm.ring_close()
+            self._ring_ready = False
+            dist.barrier(group=self.group)
+        self.rm.set_resolution(width, height)
+        if self.world_size == 1:
+            return
+        if self.gather == "p2p":
             handle = [self.rm.ipc_export_frame() if self.rank == 0 else None]
             dist.broadcast_object_list(handle, src=0, group=self.group)
             if self.rank != 0:
                 self._root_frame_ptr = self.rm.ipc_open(handle[0])
+        elif self.gather == "ring":
+            handle = [self.rm.ring_create(self.ring_slots, self.world_size) if self.rank == 0 else None]
+            dist.broadcast_object_list(handle, src=0, group=self.group)
+            if self.rank != 0:
+                self.rm.ring_open(handle[0], self.ring_slots, self.world_size)
+            self._ring_ready = True
+            self._next_view = 0
         else:
             # render into a torch-owned buffer on torch's stream so NCCL sees the same memory and ordering
             self._frame_tensor = torch.zeros(width * height, dtype=torch.int32, device=f"cuda:{self.device}")
@@ -144,7 +167,13 @@ class ShardedRenderManager:
         if self.world_size == 1:
             rm.draw_setup(setup)
             return setup
+        if self.gather == "ring":
+            self.draw_views_sharded([pose], weights=[weights])
+            return setup
         if self.gather == "p2p":
+            # the previous view is final on the root only after the barrier that ended it; whoever reads or presents it there must do
+            # so before entering this call — this barrier keeps a fast rank from storing into it any earlier than that
+            dist.barrier(group=self.group)
             rm.draw_rays(setup, begin, end)
             rm.blit_owned(setup, begin, end, self._root_frame_ptr)
             rm.sync()
@@ -156,6 +185,40 @@ class ShardedRenderManager:
             dist.reduce(self._frame_tensor, dst=0, op=dist.ReduceOp.SUM, group=self.group)  # disjoint pixels: sum == copy
         return setup
 
+    def draw_views_sharded(self, poses: Sequence[CameraPose], dst: Optional[np.ndarray] = None, weights: Optional[Sequence] = None,
+                           barrier: bool = True) -> List[FrameSetup]:
+        """A stream of views, each with its rays sharded over all ranks (gather="ring"). Every rank enqueues its share of every
+        view without waiting for anyone; the root consumes view v (into dst[v] if given: pinned host memory, one frame per view)
+        as soon as all shares of it have arrived and thereby frees its ring slot. Returns when this rank's work is done
+        (and, with `barrier`, when every rank's is)."""
+        import torch.distributed as dist
+
+        if self.gather != "ring" or not self._ring_ready:
+            raise RuntimeError("draw_views_sharded needs gather='ring' and a resolution")
+        rm = self.rm
+        setups = []
+        base = self._next_view
+        lag = self.ring_slots - 1
+        for i, pose in enumerate(poses):
+            setup = rm.make_setup(pose)
+            setups.append(setup)
+            total = sum(max(0, setup.segments[k].ray_count) for k in range(4))
+            w = weights[i] if weights is not None else ray_weights(setup, rm.width, rm.height)
+            begin, end = partition_rays(total, self.world_size, w)[self.rank]
+            rm.draw_sharded(setup, begin, end, base + i, self.rank)
+            if self.rank == 0 and i >= lag:
+                rm.ring_consume(base + i - lag, dst[i - lag] if dst is not None else None)
+        if self.rank == 0:
+            for i in range(max(0, len(poses) - lag), len(poses)):
+                rm.ring_consume(base + i, dst[i] if dst is not None else None)
+        self._next_view = base + len(poses)
+        rm.sync()
+        if self.rank == 0:
+            rm.ring_status()
+        if barrier:
+            dist.barrier(group=self.group)
+        return setups
+
     def draw_views(self, poses: Sequence[CameraPose], dst: Optional[np.ndarray] = None) -> List[int]:
         """Batched views: this rank renders views rank, rank+N, ...; returns their indices (frames land in `dst`, one
         W*H slab per local view, if given)."""
@@ -166,6 +229,7 @@ class ShardedRenderManager:
         return mine
 
     def read_frame(self) -> np.ndarray:
+        """The last single view on the root (p2p / reduce). Ring views are delivered through draw_views_sharded(dst=...)."""
         if self._frame_tensor is not None:
             import torch
             torch.cuda.current_stream(self.device).synchronize()
@@ -173,7 +237,14 @@ class ShardedRenderManager:
         return self.rm.read_frame()
 
     def destroy(self):
+        import torch.distributed as dist
+
         if self._root_frame_ptr:
             self.rm.ipc_close(self._root_frame_ptr)
             self._root_frame_ptr = 0
+        if self._ring_ready and self.world_size > 1:
+            if self.rank != 0:
+                self.rm.ring_close()
+            dist.barrier(group=self.group)   # mappings are closed before the root frees the ring
+            self._ring_ready = False
         self.rm.destroy()

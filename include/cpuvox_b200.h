@@ -194,6 +194,22 @@ int cvx_ipc_export_frame(cvx_ctx* ctx, uint8_t out_handle[CVX_IPC_HANDLE_BYTES])
 int cvx_ipc_open(cvx_ctx* ctx, const uint8_t handle[CVX_IPC_HANDLE_BYTES], void** out_device_ptr);
 int cvx_ipc_close(cvx_ctx* ctx, void* device_ptr);
 
+/* Frame ring: the pipelined form of the same gather, for a stream of ray-sharded views. The root allocates `slots` framebuffers
+ * plus flag words in ONE device allocation and exports it; every other rank maps it. For view v every rank calls cvx_draw_sharded
+ * with its flat-ray range: Phase 1 for those rays, Phase 2 for the pixels they feed, stored into ring frame v % slots on the root
+ * (NVLink peer stores), then a flag store. All ordering between ranks is on the device — a rank waits for "slot released" before
+ * it stores, the root's consumer waits for "all ranks arrived" — so no host barrier and no collective sits between two views
+ * (the reference's analogue of the unit of work is RenderManager.cs:358-363: one frame's rays as one parallel job).
+ * A wait gives up after 4 s and raises the ring's error flag (cvx_ring_status) instead of hanging the GPU. Set the resolution
+ * before creating / opening a ring; cvx_set_resolution and cvx_destroy close it (close the mappings before the root frees). */
+int cvx_ring_create(cvx_ctx* ctx, int32_t slots, int32_t world_size, uint8_t out_handle[CVX_IPC_HANDLE_BYTES]);
+int cvx_ring_open(cvx_ctx* ctx, const uint8_t handle[CVX_IPC_HANDLE_BYTES], int32_t slots, int32_t world_size);
+int cvx_ring_close(cvx_ctx* ctx);
+int cvx_draw_sharded(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t ray_begin, int32_t ray_end, int64_t view_index, int32_t rank);
+/* Root: wait for view_index from all ranks, copy it to dst_host (optional, pinned), release the slot; asynchronous (cvx_sync). */
+int cvx_ring_consume(cvx_ctx* ctx, int64_t view_index, void* dst_host, void** out_device_frame);
+int cvx_ring_status(cvx_ctx* ctx);
+
 /* Debug: dump the per-ray state after RaySetupJob/DDASetupJob/TraceToFirstColumnJob
  * (DrawSegmentRayJob.cs:12-144) for every flat ray index; 18 x 4 bytes per ray, see cvx_ray_state. */
 typedef struct cvx_ray_state {
