@@ -943,20 +943,36 @@ int cvx_draw_sharded(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t ray_beg
     cvxd_frame f;
     make_frame(ctx, setup, f);
     f.td = slot_td(ctx, slot); f.lr = slot_lr(ctx, slot);
-    if (ray_end < 0 || ray_end > f.total_rays) ray_end = f.total_rays;
-    if (ray_begin < 0) ray_begin = 0;
+    const bool interleaved = ray_begin == CVX_SHARD_INTERLEAVED;
+    if (interleaved) {
+        // rays dealt in chunks of `ray_end` rays, chunk c to rank c mod world: heavy rays come in runs of neighbouring rays, so every
+        // rank gets its share of them without any cost estimate; the launch covers the rank's local rays [0, n)
+        const int chunk = ray_end;
+        if (chunk < 1 || (chunk & (chunk - 1))) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "interleaved sharding needs a power-of-two chunk size (got %d)", chunk);
+        const int world = ctx->ringWorld;
+        const int fullRounds = f.total_rays / (chunk * world), rest = f.total_rays % (chunk * world);
+        int n = fullRounds * chunk;
+        const int mine = rest - rank * chunk;
+        n += mine <= 0 ? 0 : (mine < chunk ? mine : chunk);
+        f.il_chunk = chunk; f.il_ranks = world; f.il_rank = rank;
+        ray_begin = 0; ray_end = n;
+    } else {
+        if (ray_end < 0 || ray_end > f.total_rays) ray_end = f.total_rays;
+        if (ray_begin < 0) ray_begin = 0;
+    }
     f.ray_begin = ray_begin; f.ray_end = ray_end;
     ring_flags* fl = ring_flag_block(ctx, rslot);
-    if (view_index >= ctx->ringSlots) {  // the slot still holds view_index - slots until the root releases it
+    CU(ctx, cvxd_launch_phase1(ctx->world, f, ctx->groupSize, stream));   // Phase 1 writes this rank's own raybuffers: no need to wait for the ring
+    if (ray_end > ray_begin) ctx->launches++;
+    if (view_index >= ctx->ringSlots) {  // the ring frame still holds view_index - slots until the root releases it
         ring_wait_kernel<<<1, 32, 0, stream>>>(&fl->released, 1, (uint32_t)(view_index - ctx->ringSlots + 1), &fl->error);
         ctx->launches++;
     }
-    CU(ctx, cvxd_launch_phase1(ctx->world, f, ctx->groupSize, stream));
-    if (ray_end > ray_begin) ctx->launches++;
     cvxd_blit b;
     make_blit(ctx, f, ring_frame(ctx, rslot), b);
     b.td = f.td; b.lr = f.lr;
     b.ray_begin = ray_begin; b.ray_end = ray_end; b.owned_only = 1;
+    b.il_chunk = f.il_chunk; b.il_ranks = f.il_ranks; b.il_rank = f.il_rank;
     CU(ctx, cvxd_launch_phase2(b, stream));
     ring_signal_kernel<<<1, 1, 0, stream>>>(&fl->arrive[rank], (uint32_t)(view_index + 1));
     ctx->launches += 2;

@@ -75,6 +75,8 @@ struct cvxd_frame {
     int32_t width, height;
     int32_t total_rays;
     int32_t ray_begin, ray_end;     /* flat ray indices drawn by this launch (RaySetupJob order) */
+    int32_t il_chunk, il_ranks, il_rank; /* il_chunk > 0: rays are dealt in chunks of il_chunk (chunk c -> rank c mod il_ranks) and this
+                                     launch draws rank il_rank's; ray_begin / ray_end then count the rank's LOCAL rays [0, n) */
     uint32_t* td;                   /* top/down raybuffer: rows of `height` pixels */
     uint32_t* lr;                   /* left/right raybuffer: rows of `width` pixels */
     cvxd_counters* counters;        /* may be null */
@@ -89,6 +91,7 @@ struct cvxd_blit {
     int32_t row_begin, row_end;     /* screen rows written */
     int32_t ray_begin, ray_end;     /* only pixels sourced from these flat rays are written when `owned_only` */
     int32_t owned_only;
+    int32_t il_chunk, il_ranks, il_rank; /* il_chunk > 0: ownership is "chunk (flat / il_chunk) belongs to rank il_rank" instead of the range */
     const uint32_t* td;
     const uint32_t* lr;
     uint32_t* frame;

@@ -360,8 +360,12 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
     const int gshift = lane & ~(G - 1);     // first lane of the group inside the warp
     const uint32_t gmask = GBITS << gshift;
     const int group = threadIdx.x / G;
-    const int flat = f.ray_begin + blockIdx.x * GROUPS_PER_CTA + group;
+    int flat = f.ray_begin + blockIdx.x * GROUPS_PER_CTA + group;
     if (flat >= f.ray_end) return;
+    if (f.il_chunk > 0) {  // interleaved sharding: local ray j of this rank is ray j % chunk of the rank's (j / chunk)-th chunk
+        flat = ((flat / f.il_chunk) * f.il_ranks + f.il_rank) * f.il_chunk + (flat & (f.il_chunk - 1));
+        if (flat >= f.total_rays) return;
+    }
 #define GBALLOT(p) ((__ballot_sync(gmask, (p)) >> gshift) & GBITS)
 #define GSHFL(v, src) __shfl_sync(gmask, (v), (src), G)
 
@@ -1057,7 +1061,11 @@ __device__ __forceinline__ int p2_row(const cvxd_blit& p, const P2Seg& g, float 
     int row = f2i(floorf(v * g.rowsF));
     row = max(g.off01, min(g.off01 + g.rc - 1, row));
     owned = true;
-    if (OWNED) { const int flat = g.flatBase + row - g.off01; owned = flat >= p.ray_begin && flat < p.ray_end; }
+    if (OWNED) {
+        const int flat = g.flatBase + row - g.off01;
+        // interleaved: chunk (a power of two) c = flat / chunk belongs to rank c mod ranks
+        owned = p.il_chunk > 0 ? (int)((uint32_t)(flat >> (31 - __clz(p.il_chunk))) % (uint32_t)p.il_ranks) == p.il_rank : (flat >= p.ray_begin && flat < p.ray_end);
+    }
     return row;
 }
 template <bool OWNED>

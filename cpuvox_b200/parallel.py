@@ -132,6 +132,10 @@ class ShardedRenderManager:
             dist.barrier(group=self.group)
         self.rm.set_resolution(width, height)
         if self.world_size == 1:
+            if self.gather == "ring":   # a ring of one rank: the same code path, no mapping to exchange
+                self.rm.ring_create(self.ring_slots, 1)
+                self._ring_ready = True
+                self._next_view = 0
             return
         if self.gather == "p2p":
             handle = [self.rm.ipc_export_frame() if self.rank == 0 else None]
@@ -164,7 +168,7 @@ class ShardedRenderManager:
         if weights is None:
             weights = ray_weights(setup, rm.width, rm.height)
         begin, end = partition_rays(total, self.world_size, weights)[self.rank]
-        if self.world_size == 1:
+        if self.world_size == 1 and self.gather != "ring":
             rm.draw_setup(setup)
             return setup
         if self.gather == "ring":
@@ -186,11 +190,12 @@ class ShardedRenderManager:
         return setup
 
     def draw_views_sharded(self, poses: Sequence[CameraPose], dst: Optional[np.ndarray] = None, weights: Optional[Sequence] = None,
-                           barrier: bool = True) -> List[FrameSetup]:
+                           barrier: bool = True, chunk: int = 32, sync: bool = True) -> List[FrameSetup]:
         """A stream of views, each with its rays sharded over all ranks (gather="ring"). Every rank enqueues its share of every
         view without waiting for anyone; the root consumes view v (into dst[v] if given: pinned host memory, one frame per view)
         as soon as all shares of it have arrived and thereby frees its ring slot. Returns when this rank's work is done
-        (and, with `barrier`, when every rank's is)."""
+        (and, with `barrier`, when every rank's is); with sync=False it returns as soon as the work is enqueued (sync_views waits). Rays are dealt to the ranks in chunks of `chunk` rays unless `weights`
+        (per-ray cost estimates, one array per view) are given or chunk == 0: then each rank takes one contiguous, weight-balanced range."""
         import torch.distributed as dist
 
         if self.gather != "ring" or not self._ring_ready:
@@ -202,22 +207,33 @@ class ShardedRenderManager:
         for i, pose in enumerate(poses):
             setup = rm.make_setup(pose)
             setups.append(setup)
-            total = sum(max(0, setup.segments[k].ray_count) for k in range(4))
-            w = weights[i] if weights is not None else ray_weights(setup, rm.width, rm.height)
-            begin, end = partition_rays(total, self.world_size, w)[self.rank]
-            rm.draw_sharded(setup, begin, end, base + i, self.rank)
+            if weights is None and chunk > 0:
+                # rays dealt in chunks of `chunk` (chunk c -> rank c mod N): balanced without a cost estimate
+                rm.draw_sharded(setup, -1, chunk, base + i, self.rank)
+            else:
+                total = sum(max(0, setup.segments[k].ray_count) for k in range(4))
+                w = weights[i] if weights is not None else ray_weights(setup, rm.width, rm.height)
+                begin, end = partition_rays(total, self.world_size, w)[self.rank]
+                rm.draw_sharded(setup, begin, end, base + i, self.rank)
             if self.rank == 0 and i >= lag:
                 rm.ring_consume(base + i - lag, dst[i - lag] if dst is not None else None)
         if self.rank == 0:
             for i in range(max(0, len(poses) - lag), len(poses)):
                 rm.ring_consume(base + i, dst[i] if dst is not None else None)
         self._next_view = base + len(poses)
-        rm.sync()
-        if self.rank == 0:
-            rm.ring_status()
-        if barrier:
-            dist.barrier(group=self.group)
+        if sync:
+            self.sync_views(barrier)
         return setups
+
+    def sync_views(self, barrier: bool = True):
+        """Wait for everything draw_views_sharded(sync=False) enqueued on this rank (and, with `barrier`, on every rank)."""
+        import torch.distributed as dist
+
+        self.rm.sync()
+        if self.rank == 0:
+            self.rm.ring_status()
+        if barrier and self.world_size > 1:
+            dist.barrier(group=self.group)
 
     def draw_views(self, poses: Sequence[CameraPose], dst: Optional[np.ndarray] = None) -> List[int]:
         """Batched views: this rank renders views rank, rank+N, ...; returns their indices (frames land in `dst`, one

@@ -205,6 +205,10 @@ int cvx_ipc_close(cvx_ctx* ctx, void* device_ptr);
 int cvx_ring_create(cvx_ctx* ctx, int32_t slots, int32_t world_size, uint8_t out_handle[CVX_IPC_HANDLE_BYTES]);
 int cvx_ring_open(cvx_ctx* ctx, const uint8_t handle[CVX_IPC_HANDLE_BYTES], int32_t slots, int32_t world_size);
 int cvx_ring_close(cvx_ctx* ctx);
+/* ray_begin >= 0: this rank draws the flat rays [ray_begin, ray_end). ray_begin == CVX_SHARD_INTERLEAVED: the rays are dealt to the
+ * ranks in chunks of `ray_end` rays (a power of two; chunk c to rank c mod world_size) and this rank draws its chunks — heavy rays come in runs of
+ * neighbours, so this balances the ranks without a cost estimate. */
+#define CVX_SHARD_INTERLEAVED (-1)
 int cvx_draw_sharded(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t ray_begin, int32_t ray_end, int64_t view_index, int32_t rank);
 /* Root: wait for view_index from all ranks, copy it to dst_host (optional, pinned), release the slot; asynchronous (cvx_sync). */
 int cvx_ring_consume(cvx_ctx* ctx, int64_t view_index, void* dst_host, void** out_device_frame);

@@ -63,7 +63,8 @@ def main():
         for rep in range(2):
             if rank == 0:
                 dst[:] = 0
-            srm.draw_views_sharded(poses, dst)
+            # rep 0: rays dealt in chunks of 32 (interleaved); rep 1: one contiguous, weight-balanced range per rank
+            srm.draw_views_sharded(poses, dst, chunk=32 if rep == 0 else 0)
             if rank == 0:
                 for i, pose in enumerate(poses):
                     same = np.array_equal(dst[i], want(pose, W, H))
