@@ -103,6 +103,9 @@ def lib():
         L.ref_built_world_info.argtypes = [P, P, P, P, P]
         L.ref_built_world_copy_blob.argtypes = [P, C.c_int32, P, C.c_int64]
         L.ref_built_world_free.argtypes = [P]
+        L.ref_built_world_save.argtypes = [P, C.c_char_p]
+        L.ref_world_load.restype = P
+        L.ref_world_load.argtypes = [C.c_char_p, P, P]
         L.ref_hardware_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -208,7 +211,20 @@ def dda_walk(start, direction, lod_distances, far_clip, max_steps=100000):
     return cells[:n], dists[:n]
 
 
-def build_world_from_mesh(positions, colors32, indices, max_dimension, flips=(True, False, False), lods=LODS):
+def load_world_file(path) -> "RefWorld":
+    """WorldSaveFile.Deserialize (WorldSaveFile.cs:57-93) by the reference's own code."""
+    L = lib()
+    dims = (C.c_int32 * 3)()
+    n = C.c_int32()
+    h = L.ref_world_load(str(path).encode(), dims, C.byref(n))
+    if not h:
+        raise RuntimeError("ref_world_load: " + L.ref_last_error().decode())
+    w = RefWorld.__new__(RefWorld)
+    w.dims, w._blobs, w._w, w.world_count = tuple(dims), [], C.c_void_p(h), n.value
+    return w
+
+
+def build_world_from_mesh(positions, colors32, indices, max_dimension, flips=(True, False, False), lods=LODS, save_to=None):
     """UnityManager's Convert button (UnityManager.cs:340-366) with the reference's own builder: returns (dims, blobs, column_counts, voxels)."""
     L = lib()
     v = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
@@ -226,6 +242,8 @@ def build_world_from_mesh(positions, colors32, indices, max_dimension, flips=(Tr
         ccs = (C.c_int32 * LODS)()
         vox = (C.c_int32 * LODS)()
         L.ref_built_world_info(h, dims, nbytes, ccs, vox)
+        if save_to is not None:   # WorldSaveFile.Serialize of exactly these worlds
+            _check(L.ref_built_world_save(h, str(save_to).encode()), "ref_built_world_save")
         blobs = []
         for j in range(lods):
             b = np.zeros(nbytes[j], dtype=np.uint8)

@@ -42,7 +42,7 @@ FILES = [
     ("Assets/Code/Rendering/RayBuffer.cs", {}),
     ("Assets/Code/RenderManager.cs", {"RenderManager": ["ClearRayBuffer"]}),
     ("Assets/Code/Rendering/DrawSegmentRayJob.cs", {}),
-    ("Assets/Code/WorldSaveFile.cs", {"WorldSaveFile": "ONLY:Header"}),
+    ("Assets/Code/WorldSaveFile.cs", {}),
 ]
 
 # reference (class) types: variables of these types are references in the C++ text
@@ -52,7 +52,7 @@ CLASS_TYPES = {"RayBuffer", "Camera", "Transform", "SimpleMesh", "WorldBuilder",
 SHIM_TYPES = {
     "Allocator", "NativeArrayOptions", "UnsafeUtility", "Mathf", "Vector2", "Vector3", "Vector4", "Matrix4x4", "Quaternion",
     "Debug", "Profiler", "Color", "Color32", "float4x4", "math", "TextureFormat", "RenderTextureFormat", "FilterMode", "Object",
-    "Interlocked", "Environment", "Parallel", "Texture2D", "Screen", "MeshTopology", "CameraEvent",
+    "Interlocked", "Environment", "Parallel", "Texture2D", "Screen", "MeshTopology", "CameraEvent", "MemoryMappedFile", "FileMode",
 }
 SHIM_PROPERTIES = {"Count"}
 KEYWORDS = {"if", "else", "while", "for", "foreach", "switch", "return", "new", "do", "try", "catch", "finally", "lock", "using",
@@ -364,7 +364,7 @@ def apply_selection(t: TypeDecl, sel):
 def conv_type(ty: str, ctx: Ctx, scope: TypeDecl | None) -> str:
     """C# type text -> C++ type text (mangled nested names, arrays, class references handled by the caller)"""
     ty = ty.strip()
-    ty = re.sub(r"\b(?:Unity\.Mathematics|System\.Threading\.Tasks|System\.Threading|System\.Collections\.Generic|Unity\.Collections|UnityEngine\.Rendering|UnityEngine)\.", "", ty)
+    ty = re.sub(r"\b(?:Unity\.Mathematics|System\.Threading\.Tasks|System\.Threading|System\.Collections\.Generic|System\.IO|Unity\.Collections|UnityEngine\.Rendering|UnityEngine)\.", "", ty)
     ty = qualify_types(ty, ctx, scope)
     ty = re.sub(r"(\b\w+<[\w:,\s*]+>)\.(?=[A-Z])", r"\1::", ty)
     # T[] -> ManagedArray<T>
@@ -624,7 +624,7 @@ def conv_try(text: str) -> str:
 
 def conv_expr_text(text: str, ctx: Ctx, scope, owner_statics=None) -> str:
     """token level rewrites shared by bodies, initialisers and default values"""
-    text = re.sub(r"\b(?:Unity\.Mathematics|System\.Threading\.Tasks|System\.Threading|System\.Collections\.Generic|Unity\.Collections|UnityEngine\.Rendering|UnityEngine\.Profiling|UnityEngine)\.", "", text)
+    text = re.sub(r"\b(?:Unity\.Mathematics|System\.Threading\.Tasks|System\.Threading|System\.Collections\.Generic|System\.IO|Unity\.Collections|UnityEngine\.Rendering|UnityEngine\.Profiling|UnityEngine)\.", "", text)
     text = conv_new(text, ctx, scope)
     text = hoist_out_vars(text, ctx, scope)
     text = conv_try(text)
@@ -646,6 +646,7 @@ def conv_expr_text(text: str, ctx: Ctx, scope, owner_statics=None) -> str:
     text = re.sub(r"\bstackalloc\s+(\w+)\s*\[([^\]]+)\]", r"cs_stackalloc(\1, \2)", text)
     # statements
     text = re.sub(r"\bfixed\s*\(\s*([\w*.]+\s+\w+)\s*=\s*([\w.]+)\s*\)\s*\{", r"{ \1 = (\2).data();", text)
+    text = re.sub(r"\busing\s*\(\s*((?:[^()]|\((?:[^()]|\([^()]*\))*\))*)\)\s*\{", r"{ \1;", text)   # using (T x = ...) { -> scoped object
     text = re.sub(r"\bforeach\s*\(\s*(?:var|[\w.<>]+)\s+(\w+)\s+in\s+", r"for (auto& \1 : ", text)
     text = re.sub(r"\bvar\b", "auto", text)
     text = re.sub(r"\block\s*\([^()]*\)\s*\{", "{", text)

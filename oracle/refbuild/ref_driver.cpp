@@ -360,6 +360,32 @@ int ref_built_world_copy_blob(const ref_built_world* b, int32_t lod, void* dst, 
     memcpy(dst, bw->lods[lod].Storage.GetStartPointer(), (size_t)bytes);
     return 0;
 }
+// f1: WorldSaveFile.Serialize (WorldSaveFile.cs:8-55) of the built LODs — a .world file written by the reference's own code
+int ref_built_world_save(const ref_built_world* b, const char* path) {
+    REF_TRY
+    ref_built_world* bw = const_cast<ref_built_world*>(b);
+    for (int j = 0; j < REF_LOD_LEVELS; j++)
+        if (!bw->lods[j].Exists()) { g_err = "Serialize needs all LODs (UnityManager.cs:358-366 builds six)"; return -1; }
+    WorldSaveFile::Serialize(bw->lods, string(path));
+    return 0;
+    REF_CATCH(-9)
+}
+// WorldSaveFile.Deserialize (WorldSaveFile.cs:57-93): the worlds it returns, ready for ref_render_raybuffers / ref_draw_world
+ref_world* ref_world_load(const char* path, int32_t out_dims[3], int32_t* out_world_count) {
+    try {
+        ManagedArray<World> worlds = WorldSaveFile::Deserialize(string(path));
+        ref_world* w = new ref_world();
+        w->dims = worlds[0].Dimensions();
+        for (int j = 0; j < worlds.Length && j < REF_LOD_LEVELS; j++) w->lods[j] = worlds[j];
+        out_dims[0] = w->dims.x; out_dims[1] = w->dims.y; out_dims[2] = w->dims.z;
+        *out_world_count = worlds.Length;
+        return w;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
 void ref_built_world_free(ref_built_world* b) {
     if (!b) return;
     for (int j = 0; j < REF_LOD_LEVELS; j++)

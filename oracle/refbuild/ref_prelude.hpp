@@ -4,6 +4,56 @@
 namespace cpuvox_ref {
 template <class A, class B>
 inline int cs_compare(A a, B b) { return a < b ? -1 : (a > b ? 1 : 0); }
+
+// System.IO.MemoryMappedFiles / FileInfo as WorldSaveFile.cs uses them: a file mapped with mmap; the objects unmap / close in their
+// destructors (`using (...) { }` becomes a scope)
+}  // namespace cpuvox_ref
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+namespace cpuvox_ref {
+enum class FileMode { CreateNew = 1, Create = 2, Open = 3 };
+struct FileInfo {
+    long Length = 0;
+    explicit FileInfo(const string& path) {
+        struct stat st;
+        if (stat(path.c_str(), &st) != 0) throw cs_exception("FileNotFoundException");
+        Length = (long)st.st_size;
+    }
+};
+struct SafeMemoryMappedViewHandle_ {
+    byte* base = nullptr;
+    void AcquirePointer(byte*& p) { p = base; }
+    void ReleasePointer() {}
+};
+struct MemoryMappedViewAccessor {
+    SafeMemoryMappedViewHandle_ SafeMemoryMappedViewHandle;
+};
+struct MemoryMappedFile {
+    int fd = -1;
+    byte* base = nullptr;
+    long size = 0;
+    MemoryMappedFile() {}
+    MemoryMappedFile(const MemoryMappedFile&) = delete;
+    MemoryMappedFile(MemoryMappedFile&& o) : fd(o.fd), base(o.base), size(o.size) { o.fd = -1; o.base = nullptr; }
+    static MemoryMappedFile CreateFromFile(const string& path, FileMode mode, std::nullptr_t, long capacity) {
+        MemoryMappedFile f;
+        f.fd = open(path.c_str(), mode == FileMode::Open ? O_RDWR : (O_RDWR | O_CREAT | O_TRUNC), 0644);
+        if (f.fd < 0) throw cs_exception("IOException: cannot open file");
+        if (mode != FileMode::Open && ftruncate(f.fd, capacity) != 0) throw cs_exception("IOException: ftruncate");
+        f.size = capacity;
+        void* p = mmap(nullptr, (size_t)capacity, PROT_READ | PROT_WRITE, MAP_SHARED, f.fd, 0);
+        if (p == MAP_FAILED) throw cs_exception("IOException: mmap");
+        f.base = (byte*)p;
+        return f;
+    }
+    MemoryMappedViewAccessor CreateViewAccessor() { MemoryMappedViewAccessor a; a.SafeMemoryMappedViewHandle.base = base; return a; }
+    ~MemoryMappedFile() {
+        if (base) { msync(base, (size_t)size, MS_SYNC); munmap(base, (size_t)size); }
+        if (fd >= 0) close(fd);
+    }
+};
 }  // namespace cpuvox_ref
 
 // ---------------------------------------------------------------------------------------------------------------------

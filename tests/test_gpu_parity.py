@@ -11,7 +11,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import COMB_POSES, MILL, POSES, ROOT, comb_world, crc, irregular_world, limited, pose_for, setup_for
+from conftest import COMB_POSES, MILL, POSES, ROOT, comb_world, crc, irregular_world, limited, parse_obj, pose_for, setup_for
 from rle import encode_world
 
 pytestmark = pytest.mark.gpu
@@ -185,6 +185,36 @@ def test_mill_1024_matches_the_translated_reference_1080p(cv, ref, rm):
         rtd, rlr = ref.render_raybuffers(rw, ref.copy_setup(s), W, H)
         assert np.array_equal(td, rtd) and np.array_equal(lr, rlr), i
     rm.set_counters(True)
+
+
+def test_world_file_written_by_the_reference_uploads_and_renders(cv, ref, orc, rm, tmp_path):
+    """f1 on the device: datasets/mill.obj -> the reference's own voxelizer / builder / WorldSaveFile.Serialize (oracle/_ref) ->
+    .world file -> cvx_world_file_read -> cvx_world_upload -> frames bit-equal to the directly built world's and to the oracle's;
+    and the library's own writer/reader round trip gives the same frames."""
+    P, Cc = parse_obj(MILL)
+    path = tmp_path / "mill256_ref.world"
+    dims, blobs, ccs, vox = ref.build_world_from_mesh(P, Cc, np.arange(P.shape[0]), 256, save_to=path)
+    loaded = cv.World.load(str(path))
+    direct = cv.World.from_obj(MILL, 256)
+    path2 = tmp_path / "mill256_ours.world"
+    direct.save(str(path2))
+    again = cv.World.load(str(path2))
+    ow = orc.OracleWorld(loaded.dims, loaded.blobs, loaded.column_counts)
+    W, H = 333, 217
+    rm.set_resolution(W, H)
+    frames = []
+    for w in (loaded, direct, again):
+        rm.upload_world(w)
+        got = []
+        for spec in POSES[:5]:
+            s = setup_for(cv, direct, spec, W, H)
+            g = _gpu_frame(rm, s, 0)
+            if w is loaded:
+                _assert_same(g, _oracle_frame(orc, ow, s, W, H, 0), f".world from the reference, {spec[0]}")
+            got.append(g[3])
+        frames.append(got)
+    for a, b, c in zip(*frames):
+        assert np.array_equal(a, b) and np.array_equal(a, c)
 
 
 def test_counters_off_gives_identical_pixels(cv, rm, mill_world):

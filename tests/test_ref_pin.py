@@ -231,3 +231,28 @@ def test_mill_benchmark_path_equals_the_reference(cv, orc, ref):
     for i in range(0, 60, 5):
         s = cv.frame_setup(poses[i], W, H, lods, w.dims[1])
         _same_raybuffers(orc, ref, ow, rw, s, W, H, i)
+
+
+def test_world_file_interop_with_the_reference(cv, orc, ref, tmp_path):
+    """f1: a .world written by the reference's own WorldSaveFile.Serialize (from worlds its own builder made of datasets/mill.obj)
+    is read by the library's reader with every blob intact, the library's writer produces the same file byte for byte, and the
+    reference's Deserialize of the library-written file renders the same raybuffers."""
+    P, Cc = parse_obj(MILL)
+    ref_file, our_file = tmp_path / "mill_ref.world", tmp_path / "mill_ours.world"
+    dims, blobs, ccs, vox = ref.build_world_from_mesh(P, Cc, np.arange(P.shape[0]), 128, save_to=ref_file)
+    w = cv.World.load(str(ref_file))
+    assert tuple(w.dims) == tuple(dims) and len(w.blobs) == 6
+    for j in range(6):
+        assert np.asarray(w.blobs[j]).tobytes() == blobs[j].tobytes(), j
+        assert w.column_counts[j] == ccs[j]
+    cv.World.from_obj(MILL, 128).save(str(our_file))
+    assert open(ref_file, "rb").read() == open(our_file, "rb").read()
+    rw = ref.load_world_file(our_file)
+    assert rw.dims == tuple(dims) and rw.world_count == 6
+    ow = orc.OracleWorld(w.dims, w.blobs, w.column_counts)
+    W, H = 320, 180
+    for spec in POSES[:5]:
+        s = setup_for(cv, w, spec, W, H)
+        td, lr, _ = orc.render_raybuffers(ow, orc.copy_setup(s), W, H, threads=2)
+        rtd, rlr = ref.render_raybuffers(rw, ref.copy_setup(s), W, H, threads=2)
+        assert (td == rtd).all() and (lr == rlr).all(), spec[0]
