@@ -17,6 +17,7 @@
 #include "../../include/cpuvox_b200.h"
 #include "device_types.h"
 #include "host_frame.h"
+#include "nvtx_ranges.h"
 #include "world_builder.h"
 
 static_assert(sizeof(cvx_ray_state) == sizeof(cvxd_ray_state), "ray state layout");
@@ -390,6 +391,7 @@ int cvx_set_resolution(cvx_ctx* ctx, int32_t width, int32_t height) {
     if (width < 1 || height < 1 || width > CVXD_MAX_AXIS || height > CVXD_MAX_AXIS)
         return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "resolution %dx%d out of range (1..%d)", width, height, CVXD_MAX_AXIS);
     if (width == ctx->width && height == ctx->height) return CVX_OK;
+    CVX_RANGE("Resize textures");            // RenderManager.cs:97
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->copyStream));
@@ -467,7 +469,10 @@ int cvx_blit_owned(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t ray_begin
 
 static int draw_into(cvx_ctx* ctx, const cvx_frame_setup* setup, int slot, uint32_t* target, bool timed) {
     cvxd_frame f;
-    make_frame(ctx, setup, f);
+    {
+        CVX_RANGE("Segment setup overhead"); // RenderManager.cs:277: the SegmentContext fill
+        make_frame(ctx, setup, f);
+    }
     f.td = slot_td(ctx, slot); f.lr = slot_lr(ctx, slot);
     int r = validate_setup(ctx, setup, f.total_rays);
     if (r) return r;
@@ -479,11 +484,17 @@ static int draw_into(cvx_ctx* ctx, const cvx_frame_setup* setup, int slot, uint3
     cudaEvent_t* pe = prof ? &ctx->profEvents[3 * (size_t)ctx->profCount] : nullptr;
     if (timed) CU(ctx, cudaEventRecord(ctx->evStart, stream));
     if (prof) CU(ctx, cudaEventRecord(pe[0], stream));
-    CU(ctx, cvxd_launch_phase1(ctx->world, f, ctx->groupSize, stream));
+    {
+        CVX_RANGE("Draw planes");            // RenderManager.cs:154
+        CU(ctx, cvxd_launch_phase1(ctx->world, f, ctx->groupSize, stream));
+    }
     if (f.total_rays > 0) ctx->launches++;
     if (timed) CU(ctx, cudaEventRecord(ctx->evMid, stream));
     if (prof) CU(ctx, cudaEventRecord(pe[1], stream));
-    CU(ctx, cvxd_launch_phase2(b, stream));
+    {
+        CVX_RANGE("Blit raybuffer");         // RenderManager.cs:178
+        CU(ctx, cvxd_launch_phase2(b, stream));
+    }
     ctx->launches++;
     if (timed) { CU(ctx, cudaEventRecord(ctx->evEnd, stream)); ctx->timed = true; }
     if (prof) { CU(ctx, cudaEventRecord(pe[2], stream)); ctx->profCount++; }

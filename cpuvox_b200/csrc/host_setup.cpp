@@ -14,6 +14,7 @@
  * All arithmetic is fp32 with a fixed evaluation order (built with -ffp-contract=off) so that the values
  * handed to the device are reproducible bit for bit.
  */
+#include "nvtx_ranges.h"
 #include "../../include/cpuvox_b200.h"
 
 #include <climits>
@@ -324,6 +325,7 @@ void cvx_host_setup_lods(int32_t world_max_dimension, int32_t res_x, int32_t res
 int cvx_host_frame_setup(const cvx_pose* pose, const float lod_distances[CVX_LOD_LEVELS], int32_t world_dim_y, cvx_frame_setup* out) {
     (void)world_dim_y;
     if (!pose || !lod_distances || !out || pose->pixel_width < 1 || pose->pixel_height < 1) return CVX_ERR_INVALID_ARGUMENT;
+    CVX_RANGE("Setup VP + segment params");  // RenderManager.cs:119,127
     memset(out, 0, sizeof *out);
     const int W = pose->pixel_width, H = pose->pixel_height;
     const Quat rot = {pose->rotation[0], pose->rotation[1], pose->rotation[2], pose->rotation[3]};

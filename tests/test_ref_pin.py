@@ -256,3 +256,30 @@ def test_world_file_interop_with_the_reference(cv, orc, ref, tmp_path):
         td, lr, _ = orc.render_raybuffers(ow, orc.copy_setup(s), W, H, threads=2)
         rtd, rlr = ref.render_raybuffers(rw, ref.copy_setup(s), W, H, threads=2)
         assert (td == rtd).all() and (lr == rlr).all(), spec[0]
+
+
+def test_degenerate_triangle_quirk_of_the_reference(cv, ref):
+    """A zero-area triangle makes VoxelizerHelper.GetVoxelsInternal return before it sets writtenVoxelCount (VoxelizerHelper.cs:45-47),
+    so WorldBuilder.Import (WordBuilder.cs:71-74) submits the PREVIOUS triangle's voxels of the same worker task once more — which
+    changes colour averages and depends on Environment.ProcessorCount (the task partition). The library skips such triangles
+    (= the reference whenever a degenerate triangle opens a task, and for meshes without any, like datasets/mill.obj). This test
+    pins the understanding: the reference (one task) on a soup with a degenerate triangle == the library on the same soup with that
+    triangle replaced by a copy of its predecessor."""
+    rng = np.random.default_rng(77)
+    n = 120
+    base = rng.uniform(0, 10, (n, 1, 3))
+    P = (base + rng.normal(0, 0.8, (n, 3, 3))).astype(np.float32).reshape(-1, 3)
+    C = rng.integers(0, 256, (n * 3, 4), dtype=np.uint8)
+    C[:, 3] = 255
+    P[30:33] = P[30]                      # triangle 10 has zero area
+    dims, blobs, ccs, vox = ref.build_world_from_mesh(P, C, np.arange(n * 3), 64, flips=(False, False, False))
+    skipped = cv.World.from_mesh(P, C, 64)
+    assert any(np.asarray(a).tobytes() != b.tobytes() for a, b in zip(skipped.blobs, blobs)), "the quirk changes colours"
+    P2, C2 = P.copy(), C.copy()
+    P2[30:33], C2[30:33] = P[27:30], C[27:30]   # the predecessor, submitted twice
+    # same bounds => same rescale: the degenerate triangle's vertex lies inside its predecessor's neighbourhood only if it does not
+    # extend the mesh bounds; build both and compare when the dimensions agree
+    dup = cv.World.from_mesh(P2, C2, 64)
+    if tuple(dup.dims) == tuple(dims) and np.array_equal(P.min(0), P2.min(0)) and np.array_equal(P.max(0), P2.max(0)):
+        for j in range(6):
+            assert np.asarray(dup.blobs[j]).tobytes() == blobs[j].tobytes(), j
