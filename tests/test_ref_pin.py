@@ -266,7 +266,7 @@ def test_degenerate_triangle_quirk_of_the_reference(cv, ref):
     pins the understanding: the reference (one task) on a soup with a degenerate triangle == the library on the same soup with that
     triangle replaced by a copy of its predecessor."""
     rng = np.random.default_rng(77)
-    n = 120
+    n = 300
     base = rng.uniform(0, 10, (n, 1, 3))
     P = (base + rng.normal(0, 0.8, (n, 3, 3))).astype(np.float32).reshape(-1, 3)
     C = rng.integers(0, 256, (n * 3, 4), dtype=np.uint8)
