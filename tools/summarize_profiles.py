@@ -54,7 +54,7 @@ WANT = [
 ]
 
 
-def full(rep):
+def full(rep, kernel="phase1", traffic_file="phase1_traffic.json"):
     p = os.path.join(ROOT, "gpurun_out", rep + ".ncu-rep")
     if not os.path.exists(p):
         return
@@ -63,7 +63,7 @@ def full(rep):
     hdr, units, data = rows[0], rows[1], rows[2:]
     stall = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("_per_issue_active.ratio") and "not_issued" not in h]
     with open(os.path.join(out, f"{tag}_{rep}.md"), "w") as f:
-        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:phase1 ({tag}, {rep})\n\n")
+        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:{kernel} ({tag}, {rep})\n\n")
         f.write("Command: `python tools/one_frame.py --res 3840x2160 --poses 30,59 --reps 2` (mill 1024^3; the captured launches are pose 59, the heaviest class of the path)\n\n")
         f.write("| metric | unit | " + " | ".join(f"launch {i}" for i in range(len(data))) + " |\n|---|---|" + "---|" * len(data) + "\n")
         for w in WANT + stall:
@@ -75,7 +75,7 @@ def full(rep):
         v = float(v.replace(",", ""))
         return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
     tr = sum(tobytes(r[i_r], units[i_r]) + tobytes(r[i_w], units[i_w]) for r in data) / len(data)
-    tp = os.path.join(out, "phase1_traffic.json")
+    tp = os.path.join(out, traffic_file)
     t = json.load(open(tp)) if os.path.exists(tp) else {}
     t["3840"] = tr
     t["_source"] = f"profiles/{tag}_{rep}.md (pose 59, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
@@ -85,5 +85,27 @@ def full(rep):
         f.write(lines)
 
 
+def instructions():
+    """profiles/phase1_inst.json: mean warp instructions per product Phase-1 launch over the 60 poses (gpurun_out/inst.csv)."""
+    p = os.path.join(ROOT, "gpurun_out", "inst.csv")
+    if not os.path.exists(p):
+        return
+    rows = [r for r in csv.reader(open(p)) if len(r) > 5]
+    hdr = next(r for r in rows if r[0] == "ID")
+    ix = {h: i for i, h in enumerate(hdr)}
+    vals = [float(r[ix["Metric Value"]].replace(",", "")) for r in rows
+            if r[0] != "ID" and r[ix["Metric Name"]] == "smsp__inst_executed.sum" and "phase1_kernel<32, 0, 0" in r[ix["Kernel Name"]].replace("(int)", "").replace("(bool)", "")]
+    vals = vals[-60:]   # the timed step's 60 product launches come last (warm-up and exclusive passes before them use the same kernel)
+    if not vals:
+        return
+    head = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    json.dump({"3840": sum(vals) / len(vals), "_per_pose_min_max": [min(vals), max(vals)],
+               "_source": f"ncu --metrics smsp__inst_executed.sum over the last 60 product Phase-1 launches of `bench.py --steps 1 --warmup 1 --no-extras` at 3840x2160 "
+                          f"(tools/gpu_round.sh, {tag}, kernel of commit {head})"},
+              open(os.path.join(out, "phase1_inst.json"), "w"), indent=1)
+
+
 launches()
+instructions()
 full("prof_phase1_4k")
+full("prof_phase2_4k", "phase2", "phase2_traffic.json")
