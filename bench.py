@@ -70,6 +70,7 @@ def parse_args():
     ap.add_argument("--inflight", type=int, default=6, help="views in flight per cvx_draw_batch (1..8)")
     ap.add_argument("--inflight-e2e", type=int, default=8, help="views in flight for the e2e leg (frame copies occupy the slots longer)")
     ap.add_argument("--ring-slots", type=int, default=8, help="framebuffers of the gather ring (--mode rays)")
+    ap.add_argument("--shard-chunk", type=int, default=512, help="--mode rays: rays are dealt to the ranks in chunks of this many (power of two)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-1080p", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip at_inflight, d2h_ceiling and rays_sharded (profiling runs)")
@@ -412,18 +413,18 @@ def d2h_ceiling(torch, dist, device, world_size, bytes_per_copy, blocks, copies=
             "note": "all ranks copying device -> pinned host at once, 4 streams each, nothing else running"}
 
 
-def time_rays(torch, dist, srm, poses, steps, warmup, device, world_size, dst=None):
+def time_rays(torch, dist, srm, poses, steps, warmup, device, world_size, dst=None, chunk=512):
     """--mode rays: a step = draw_views_sharded over the views (every view's rays cut over the ranks, frames gathered in the ring on
     rank 0). Host clock between synchronize+barrier pairs: all device work of the steps lies inside; max over ranks."""
     for _ in range(warmup):
-        srm.draw_views_sharded(poses, dst)
+        srm.draw_views_sharded(poses, dst, chunk=chunk)
     torch.cuda.synchronize(device)
     if world_size > 1:
         dist.barrier()
     launches0 = srm.rm.launch_count()
     t0 = time.perf_counter()
     for _ in range(steps):
-        srm.draw_views_sharded(poses, dst, barrier=False, sync=False)   # the ring's device-side flags order the steps: no drain between them
+        srm.draw_views_sharded(poses, dst, barrier=False, sync=False, chunk=chunk)   # the ring's device-side flags order the steps: no drain between them
     srm.sync_views(barrier=False)
     torch.cuda.synchronize(device)
     dt = time.perf_counter() - t0
@@ -473,10 +474,10 @@ def run_rays(a, rank, local_rank, world_size, torch, dist, cv, N, world, poses, 
         rm.set_counters(False)
         rm.sync()
     sampler = ClockSampler(device) if rank == 0 else None
-    dt, launches, span = time_rays(torch, dist, srm, poses, a.steps, a.warmup, device, world_size)
+    dt, launches, span = time_rays(torch, dist, srm, poses, a.steps, a.warmup, device, world_size, chunk=a.shard_chunk)
     clocks = sampler.stop(*span) if sampler else None
     pinned = cv.alloc_pinned((len(poses), H, W)) if rank == 0 else None
-    e2e_dt, _, _ = time_rays(torch, dist, srm, poses, max(2, a.steps // 2), 1, device, world_size, dst=pinned)
+    e2e_dt, _, _ = time_rays(torch, dist, srm, poses, max(2, a.steps // 2), 1, device, world_size, dst=pinned, chunk=a.shard_chunk)
     e2e_steps = max(2, a.steps // 2)
     if rank == 0:
         frames = len(poses) * a.steps
@@ -492,7 +493,7 @@ def run_rays(a, rank, local_rank, world_size, torch, dist, cv, N, world, poses, 
                 "parallelism": f"rays of every view sharded over {world_size} GPU(s); pixels stored into a ring of {a.ring_slots} framebuffers on rank 0 over NVLink "
                                "peer memory, device-side flags between ranks, no host barrier or collective between views; world broadcast once and replicated",
                 "l2": "inputs larger than L2: the raybuffers + frame of one view are 1.0 GB at 8K (no flush)" if W * H > 20e6 else "no flush: successive views differ",
-                "frames_in_flight": a.inflight, "ring_slots": a.ring_slots,
+                "frames_in_flight": a.inflight, "ring_slots": a.ring_slots, "shard_chunk_rays": a.shard_chunk,
                 "timing": "host clock between synchronize+barrier pairs around the steps (all device work inside), max over ranks"}),
             "runs_per_s": sum(c["runs_visited"] for c in per) / len(per) * fps,
             "ms_per_frame": {"total": 1000.0 * dt / frames},
@@ -603,16 +604,19 @@ def run_b200(a, rank, local_rank, world_size):
     if world_size > 1 and not a.no_extras:
         rm.destroy()
         rm = None
-        srm = cv.ShardedRenderManager(device, rank, world_size, gather="ring", ring_slots=a.ring_slots)
-        srm.upload_world(world)
-        srm.rm.set_frames_in_flight(a.inflight)
-        srm.set_resolution(W, H)
-        sub = poses[:60]
-        rdt, _, _ = time_rays(torch, dist, srm, sub, 3, 1, device, world_size)
-        rays_sharded = {"value": len(sub) * 3 / rdt, "unit": "frames/s", "views": len(sub), "scaling": "strong",
-                        "note": f"{len(sub)} views of the same workload, every view's rays cut over the {world_size} ranks, frames gathered in a ring on rank 0 "
-                                "over NVLink peer memory (device-side flags, no host barrier between views); compare with value / n_gpus-fold work"}
-        srm.destroy()
+        try:   # an extra: its failure must not cost the main line (every measurement above is already taken)
+            srm = cv.ShardedRenderManager(device, rank, world_size, gather="ring", ring_slots=a.ring_slots)
+            srm.upload_world(world)
+            srm.rm.set_frames_in_flight(a.inflight)
+            srm.set_resolution(W, H)
+            sub = poses[:60]
+            rdt, _, _ = time_rays(torch, dist, srm, sub, 3, 1, device, world_size, chunk=a.shard_chunk)
+            rays_sharded = {"value": len(sub) * 3 / rdt, "unit": "frames/s", "views": len(sub), "scaling": "strong",
+                            "note": f"{len(sub)} views of the same workload, every view's rays dealt over the {world_size} ranks in chunks of {a.shard_chunk}, frames gathered in a ring "
+                                    "on rank 0 over NVLink peer memory (device-side flags, no host barrier between views); the same total work as ONE rank's share of `value`"}
+            srm.destroy()
+        except Exception as e:  # noqa: BLE001
+            rays_sharded = {"error": str(e)[:300]}
 
     main = results[(W, H)]
     steps = main["steps"]

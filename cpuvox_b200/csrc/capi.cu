@@ -177,6 +177,7 @@ __global__ void ring_wait_kernel(const uint32_t* flags, int n, uint32_t value, u
     long long t0;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
     while ((int32_t)(ring_load(flags + i) - value) < 0) {
+        if (ring_load(error)) break;              // another wait of this ring has already given up: do not queue up more timeouts
         __nanosleep(256);
         long long t;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -976,7 +977,7 @@ int cvx_draw_sharded(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t ray_beg
     CU(ctx, cvxd_launch_phase1(ctx->world, f, ctx->groupSize, stream));   // Phase 1 writes this rank's own raybuffers: no need to wait for the ring
     if (ray_end > ray_begin) ctx->launches++;
     if (view_index >= ctx->ringSlots) {  // the ring frame still holds view_index - slots until the root releases it
-        ring_wait_kernel<<<1, 32, 0, stream>>>(&fl->released, 1, (uint32_t)(view_index - ctx->ringSlots + 1), &fl->error);
+        ring_wait_kernel<<<1, 32, 0, stream>>>(&fl->released, 1, (uint32_t)(view_index - ctx->ringSlots + 1), &ring_flag_block(ctx, 0)->error);
         ctx->launches++;
     }
     cvxd_blit b;
@@ -1002,7 +1003,7 @@ int cvx_ring_consume(cvx_ctx* ctx, int64_t view_index, void* dst_host, void** ou
     CU(ctx, cudaSetDevice(ctx->device));
     const int rslot = (int)(view_index % ctx->ringSlots);
     ring_flags* fl = ring_flag_block(ctx, rslot);
-    ring_wait_kernel<<<1, CVX_RING_MAX_RANKS, 0, ctx->copyStream>>>(fl->arrive, ctx->ringWorld, (uint32_t)(view_index + 1), &fl->error);
+    ring_wait_kernel<<<1, CVX_RING_MAX_RANKS, 0, ctx->copyStream>>>(fl->arrive, ctx->ringWorld, (uint32_t)(view_index + 1), &ring_flag_block(ctx, 0)->error);
     if (dst_host) CU(ctx, cudaMemcpyAsync(dst_host, ring_frame(ctx, rslot), ctx->ringFrameBytes, cudaMemcpyDeviceToHost, ctx->copyStream));
     ring_signal_kernel<<<1, 1, 0, ctx->copyStream>>>(&fl->released, (uint32_t)(view_index + 1));
     ctx->launches += 2;
@@ -1015,12 +1016,8 @@ int cvx_ring_consume(cvx_ctx* ctx, int64_t view_index, void* dst_host, void** ou
 int cvx_ring_status(cvx_ctx* ctx) {
     if (!ctx || !ctx->ring) return CVX_ERR_INVALID_ARGUMENT;
     CU(ctx, cudaSetDevice(ctx->device));
-    int bad = 0;
-    for (int s = 0; s < ctx->ringSlots; s++) {
-        uint32_t e = 0;
-        CU(ctx, cudaMemcpy(&e, &ring_flag_block(ctx, s)->error, 4, cudaMemcpyDeviceToHost));
-        bad |= e != 0;
-    }
+    uint32_t bad = 0;   // one error word for the whole ring (slot 0's): the first wait that times out raises it, later waits return at once
+    CU(ctx, cudaMemcpy(&bad, &ring_flag_block(ctx, 0)->error, 4, cudaMemcpyDeviceToHost));
     return bad ? fail(ctx, CVX_ERR_CUDA, "a frame-ring wait timed out (a rank did not deliver its share of a view)") : CVX_OK;
 }
 

@@ -1157,14 +1157,39 @@ phase2_kernel(const __grid_constant__ cvxd_blit p) {
             const uint32_t m = __ballot_sync(FULL_MASK, in) & 0xfu;
             if (u < 0 && m == 0xfu) u = k;
         }
+        P2Seg g;
+        if (u >= 0) g = p2_seg(p, u);
+        if (OWNED && u >= 0) {
+            // sharded mode: the ray row is monotone along any line inside one segment, so the tile's rows lie between the rows of its
+            // four corner pixels; if none of them (nor anything between) belongs to this launch the whole tile is someone else's
+            bool owned;
+            const int cx = (lane & 1) ? xLast : x0, cy = (lane & 2) ? yLast : y0;
+            const int row = p2_row_in<false>(p, g, cx, cy, owned);
+            int lo = row, hi = row;
+#pragma unroll
+            for (int o = 1; o < 4; o <<= 1) {
+                lo = min(lo, __shfl_xor_sync(FULL_MASK, lo, o));
+                hi = max(hi, __shfl_xor_sync(FULL_MASK, hi, o));
+            }
+            const int f0 = g.flatBase + lo - g.off01 - 1, f1 = g.flatBase + hi - g.off01 + 1;   // +-1: rounding at the corners
+            bool mine;
+            if (p.il_chunk > 0) {
+                const int sh = 31 - __clz(p.il_chunk);
+                const int c0 = max(f0, 0) >> sh, c1 = max(f1, 0) >> sh;
+                // chunks c0..c1: one of them is this rank's iff the span covers a multiple of ranks or wraps onto il_rank
+                mine = (c1 - c0 + 1 >= p.il_ranks) || ((p.il_rank - c0 % p.il_ranks + p.il_ranks) % p.il_ranks <= c1 - c0);
+            } else mine = f1 >= p.ray_begin && f0 < p.ray_end;
+            if (!mine) u = -2;
+        }
         if (lane == 0) {
             uniShared = u;
-            if (u >= 0) segShared = p2_seg(p, u);
+            if (u >= 0) segShared = g;
         }
     }
     if (OWNED && threadIdx.x < P2_TH * NH) ownBits[threadIdx.x] = 0u;
     __syncthreads();
     const int uni = uniShared;
+    if (uni == -2) return;   // sharded mode: no pixel of this tile is fed by this launch's rays
 
     if (uni >= 2) {
         // ---- left/right segment: lanes 8 along x, 4 along y; read and write directly. The rows first, then the gathers back

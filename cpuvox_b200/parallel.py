@@ -190,7 +190,7 @@ class ShardedRenderManager:
         return setup
 
     def draw_views_sharded(self, poses: Sequence[CameraPose], dst: Optional[np.ndarray] = None, weights: Optional[Sequence] = None,
-                           barrier: bool = True, chunk: int = 32, sync: bool = True) -> List[FrameSetup]:
+                           barrier: bool = True, chunk: int = 512, sync: bool = True) -> List[FrameSetup]:
         """A stream of views, each with its rays sharded over all ranks (gather="ring"). Every rank enqueues its share of every
         view without waiting for anyone; the root consumes view v (into dst[v] if given: pinned host memory, one frame per view)
         as soon as all shares of it have arrived and thereby frees its ring slot. Returns when this rank's work is done
