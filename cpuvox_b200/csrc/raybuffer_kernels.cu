@@ -3,23 +3,26 @@
  *
  *   phase1_kernel   one WARP per raybuffer row (ray). Replaces RaySetupJob, DDASetupJob, TraceToFirstColumnJob and
  *                   RenderJob/ExecuteRay (Assets/Code/Rendering/DrawSegmentRayJob.cs:12-620) in a single launch.
- *   phase2_kernel   one thread per screen pixel; replaces BlitSegments + RayBufferBlit.shader
+ *   phase2_kernel   one CTA per 64 x 32 screen tile; replaces BlitSegments + RayBufferBlit.shader
  *                   (Assets/Code/RenderManager.cs:199-256, Assets/Shaders/RayBufferBlit.shader:47-64).
  *
- * Design (not a translation of the per-thread C# loop):
+ * Phase 1 design (not a translation of the per-thread C# loop; DESIGN.md §3.1 has the long form):
  *  - The DDA cell sequence of a ray (including the LOD switches, SegmentDDAData.cs:31-73,135-150) does not depend on
  *    world data, so the warp walks it 32 cells ahead: every lane keeps the (uniform) DDA state, lane i captures cell i,
  *    then all 32 column headers are fetched with one 128-bit load per lane. A ballot picks the non-empty columns; only
  *    those enter the order-dependent part.
- *  - Inside a column the RLE runs are spread over lanes: a warp prefix sum gives every run its world-Y bounds, each lane
- *    projects/clips/rounds its own run's side span and cap span (the float-heavy part, none of which depends on the
- *    written-pixel state), and the spans are then committed strictly in reference order.
- *  - The per-row written-pixel set is a bitmask in shared memory (one word per 32 pixels). Pixel loops run 32 pixels
- *    per step on word-aligned groups (coalesced 128-byte stores), the mask is updated with warp ballots, and the
- *    "skip already written pixels" scans of ReducePixelHorizon (:660-697) are bit scans.
+ *  - Boundary-table kernel (FAST, regular worlds): a ROUND caches the run boundaries of several consecutive columns, one
+ *    boundary per lane; each boundary is projected once on the last and once on the next line, the side span of a run is the
+ *    pair of its two boundaries' projections, its cap span the last/next pair of one boundary. None of that depends on the
+ *    written-pixel state. Per round, ballots record which lanes' spans still hold an unwritten pixel (hot lanes); cached
+ *    columns without one are skipped, and the commit loop of an entered column walks its hot lanes in reference order.
+ *    The general kernel (!FAST, any world) keeps one run per lane with a segmented prefix sum for the world-Y extents.
+ *  - The per-row written-pixel set is a bitmask in shared memory (one word per 32 pixels). Pixels are written lane-parallel
+ *    over a span, the mask words of the span are OR-ed by one lane per word, and the "skip already written pixels" scans of
+ *    ReducePixelHorizon (:660-697) are bit scans.
  *  - Numerics: IEEE fp32, no FMA contraction (-fmad=false), IEEE division/sqrt, denormals kept (float.Epsilon sentinel
- *    of :220-221 must survive), same operation order as the reference expressions, so rows match the CPU restatement
- *    bit for bit.
+ *    of :220-221 must survive), same operation order as the reference expressions, so rows match the reference's own code
+ *    (compiled for the CPU) bit for bit.
  */
 #ifdef CVX_EMU /* test-only CPU build of this source under tools/simt_emu (never part of the product library) */
 #include "cuda_emu.h"
@@ -428,8 +431,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
         const int maskX = world.dim_x - 1, maskZ = world.dim_z - 1;
         // unlerp(0, worldMaxY, y) = (y - 0) / (worldMaxY - 0): for a power-of-two height the quotient is exactly y * 2^-k
 
-        // Side-span pixels are a colour gather followed by a store: the store is deferred until this lane's next gather (or the end
-        // of the ray), so the gather's latency is not on the ray's critical path. Nothing in this kernel reads the row back.
+        // CVXD_DEFER_STORE builds only (off: measured neutral): a side-span pixel's store waits until this lane's next gather
         int pendY = -1; uint32_t pendColor = 0u;
         bool terminated = false; // ray ended inside the loop: skybox the rest and stop
         bool reachedEnd = false; // far clip or world exit
