@@ -565,29 +565,54 @@ def test_benchmark_path_full_size(cv, orc, rm, mill_1024, res, frames):
         assert written == g[2]["px_voxel"] + g[2]["px_sky"]
 
 
-def test_large_terrain_world_config2(cv, orc, rm):
-    """BASELINE config 2 shape (procedural heightmap terrain, camera pitched down, VP on screen, 4 segments) at 1024^3."""
-    world = cv.World.synthetic(0, (1024, 1024, 1024), seed=1234)
+@pytest.fixture(scope="module")
+def terrain_2048(cv):
+    return cv.World.synthetic(0, (2048, 2048, 2048), seed=1234)
+
+
+def test_terrain_2048_configs_2_3_full_size(cv, orc, ref, rm, terrain_2048):
+    """BASELINE configs 2 and 3 at FULL size: the fBm terrain 2048^3 (seed 1234); config 2 = 1920x1080, camera at the centre, y 1700,
+    pitch 60 down (vanishing point on screen, 4 segments); config 3 = 3840x2160, 40 above the ground, pitch 3 and pitch 0
+    (LimitRotationHorizon, clamped segments). Raybuffers, counters and frame bit-exact vs the oracle, raybuffers also vs the
+    translated reference."""
+    world = terrain_2048
+    ow = orc.OracleWorld(world.dims, world.blobs, world.column_counts)
+    rw = ref.RefWorld(world.dims, world.blobs, world.column_counts)
+    rm.upload_world(world)
+    hdr = np.asarray(world.blobs[0])[: 12 * world.column_counts[0]].view(np.uint32).reshape(-1, 3)
+    ground = int(hdr[1024 * 2048 + 1024, 2] & 0xFFFF)
+    cases = [((1920, 1080), cv.CameraPose.from_euler((1024.0, 1700.0, 1024.0), (60.0, 30.0, 0.0), far_clip=4096.0), 4),
+             ((3840, 2160), cv.CameraPose.from_euler((1024.5, ground + 40.0, 1024.5), (3.0, 75.0, 0.0), far_clip=4096.0), None),
+             ((3840, 2160), cv.CameraPose.from_euler((1024.5, ground + 40.0, 1024.5), (0.0, 165.0, 0.0), far_clip=4096.0), None)]
+    for (W, H), pose, segs in cases:
+        rm.set_resolution(W, H)
+        s = rm.make_setup(pose)
+        if segs:
+            assert sum(1 for k in range(4) if s.segments[k].ray_count > 0) == segs
+        g = _gpu_frame(rm, s, 0)
+        _assert_same(g, _oracle_frame(orc, ow, s, W, H, 0), f"terrain 2048^3 {W}x{H}")
+        rtd, rlr = ref.render_raybuffers(rw, ref.copy_setup(s), W, H)
+        assert np.array_equal(g[0], rtd) and np.array_equal(g[1], rlr), f"terrain 2048^3 {W}x{H} vs the translated reference"
+
+
+def test_structure_world_config4_full_size(cv, orc, rm):
+    """BASELINE config 4 at FULL size: boxes/pipes/slabs 4096x1024x4096 (seed 7, a 4.5 GB LOD-0 blob), 7680x4320, far 8192, two of the
+    bench's four views: bit-exact vs the oracle."""
+    world = cv.World.synthetic(1, (4096, 1024, 4096), seed=7)
     ow = orc.OracleWorld(world.dims, world.blobs, world.column_counts)
     rm.upload_world(world)
-    W, H = 1920, 1080
+    W, H = 7680, 4320
     rm.set_resolution(W, H)
-    pose = cv.CameraPose.from_euler((512.0, 850.0, 512.0), (60.0, 30.0, 0.0), far_clip=2048.0)
-    s = rm.make_setup(pose)
-    assert all(s.segments[k].ray_count > 0 for k in range(4))
-    _assert_same(_gpu_frame(rm, s, 0), _oracle_frame(orc, ow, s, W, H, 0), "terrain1024 1080p")
-    # config 3 shape: near-horizontal camera, clamped segments, 4K
-    W, H = 3840, 2160
-    rm.set_resolution(W, H)
-    pose = cv.CameraPose.from_euler((512.0, 700.0, 512.0), (3.0, 30.0, 0.0), far_clip=2048.0)
-    s = rm.make_setup(pose)
-    _assert_same(_gpu_frame(rm, s, 0), _oracle_frame(orc, ow, s, W, H, 0), "terrain1024 4K pitch 3")
+    for pos, euler in (((2048.5, 700.5, 2048.5), (35.0, 20.0, 0.0)), ((3000.5, 950.5, 1000.5), (70.0, 200.0, 10.0))):
+        s = rm.make_setup(cv.CameraPose.from_euler(pos, euler, far_clip=8192.0))
+        _assert_same(_gpu_frame(rm, s, 0), _oracle_frame(orc, ow, s, W, H, 0), f"structures 4096x1024x4096 8K {pos}")
+    rm.upload_world(cv.World.synthetic(0, (64, 64, 64), seed=1))   # release the 6 GB world before the next tests
+    rm.set_resolution(320, 180)
 
 
 def test_structure_world_8k_and_batched_cameras_configs_4_5(cv, orc, rm):
-    """BASELINE config 4 shape (boxes/pipes/slabs world with many multi-run columns, 7680x4320, far 4x the world) and config 5
-    shape (seeded random cameras at 1280x720 over the terrain, rendered as one batch) at test size; the full-size runs are
-    tools/configs_check.py (results in DESIGN.md §7)."""
+    """BASELINE config 4 shape at a second, smaller size (X != Z, other camera classes) and config 5 (seeded random cameras at
+    1280x720 over the terrain, rendered as one batch) at test size; bench.py --config 4 / 5 are the full-size runs."""
     world = cv.World.synthetic(1, (1024, 256, 1024), seed=7)
     ow = orc.OracleWorld(world.dims, world.blobs, world.column_counts)
     rm.upload_world(world)
