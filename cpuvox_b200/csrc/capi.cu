@@ -17,6 +17,7 @@
 #include "../../include/cpuvox_b200.h"
 #include "device_types.h"
 #include "host_frame.h"
+#include "jpeg_encoder.h"
 #include "nvtx_ranges.h"
 #include "world_builder.h"
 
@@ -60,7 +61,9 @@ struct cvx_ctx {
     int lastSlot = 0;                   // slot of the most recent view (what the read functions return)
     cudaEvent_t evBatchStart = nullptr;
     uint32_t* externalFrame = nullptr;
-    uint32_t* presentStage = nullptr;   // cvx_present with a host destination: converted frame before the device->host copy
+    uint32_t* presentStage = nullptr;   // cvx_present with a host destination / cvx_present_jpeg: converted frame (W*H*4 bytes)
+    cvxjpeg::Encoder* jpeg = nullptr;   // created by the first cvx_present_jpeg
+    std::vector<uint8_t> jpegOut;
     int frameIndex = 0;
     cvxd_counters* counters = nullptr;
     cudaEvent_t evStart = nullptr, evMid = nullptr, evEnd = nullptr;
@@ -328,6 +331,7 @@ int cvx_destroy(cvx_ctx* ctx) {
     free_resolution(ctx);
     free_world(ctx);
     for (cudaEvent_t e : ctx->profEvents) cudaEventDestroy(e);
+    cvxjpeg::destroy(ctx->jpeg);
     cudaFree(ctx->counters);
     if (ctx->evStart) cudaEventDestroy(ctx->evStart);
     if (ctx->evMid) cudaEventDestroy(ctx->evMid);
@@ -596,10 +600,10 @@ int cvx_blit_raybuffer(cvx_ctx* ctx, int32_t which) {
 // stays there (dst_is_device: a mapped graphics resource, an encoder input surface, a peer buffer) or is copied to the host.
 int cvx_present(cvx_ctx* ctx, int32_t format, int32_t top_down, void* dst, int32_t dst_is_device) {
     if (!ctx || !dst) return ctx ? fail(ctx, CVX_ERR_INVALID_ARGUMENT, "dst is NULL") : CVX_ERR_INVALID_ARGUMENT;
-    if (format != CVX_PRESENT_RGBA8 && format != CVX_PRESENT_BGRA8) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "unknown present format %d", format);
+    if (format != CVX_PRESENT_RGBA8 && format != CVX_PRESENT_BGRA8 && format != CVX_PRESENT_RGB8) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "unknown present format %d", format);
     if (ctx->width <= 0) return fail(ctx, CVX_ERR_NO_RESOLUTION, "no resolution set");
     const int W = ctx->width, H = ctx->height;
-    const size_t fbBytes = (size_t)W * H * 4;
+    const size_t fbBytes = (size_t)W * H * 4, outBytes = (size_t)W * H * (format == CVX_PRESENT_RGB8 ? 3 : 4);
     CU(ctx, cudaSetDevice(ctx->device));
     uint32_t* out = (uint32_t*)dst;
     if (!dst_is_device) {
@@ -609,12 +613,47 @@ int cvx_present(cvx_ctx* ctx, int32_t format, int32_t top_down, void* dst, int32
         }
         out = ctx->presentStage;
     }
-    CU(ctx, cvxd_launch_present(current_target(ctx), out, W, H, format == CVX_PRESENT_BGRA8, top_down != 0, ctx->stream));
+    if (format == CVX_PRESENT_RGB8) CU(ctx, cvxd_launch_present_rgb8(current_target(ctx), (uint8_t*)out, W, H, top_down != 0, ctx->stream));
+    else CU(ctx, cvxd_launch_present(current_target(ctx), out, W, H, format == CVX_PRESENT_BGRA8, top_down != 0, ctx->stream));
     ctx->launches++;
     if (!dst_is_device) {
-        CU(ctx, cudaMemcpyAsync(dst, out, fbBytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(dst, out, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    return CVX_OK;
+}
+
+// Presentation as a compressed still: the frame is packed to top-down R,G,B bytes by present_rgb8_kernel and encoded on the device by
+// nvJPEG's CUDA encoder (jpeg_encoder.cpp; the toolkit library is loaded on first use); only the bitstream crosses to the host.
+int cvx_present_jpeg(cvx_ctx* ctx, int32_t quality, int32_t subsampling, void* dst, int64_t dst_capacity, int64_t* out_bytes) {
+    if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
+    if (!out_bytes) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "out_bytes is NULL");
+    *out_bytes = 0;
+    if (quality < 1 || quality > 100) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "JPEG quality %d: expected 1..100", quality);
+    if (subsampling != CVX_JPEG_444 && subsampling != CVX_JPEG_420) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "unknown chroma subsampling %d", subsampling);
+    if (dst_capacity < 0 || (dst_capacity > 0 && !dst)) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "bad destination buffer");
+    if (ctx->width <= 0) return fail(ctx, CVX_ERR_NO_RESOLUTION, "no resolution set");
+    const int W = ctx->width, H = ctx->height;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->jpeg) {
+        std::string err;
+        ctx->jpeg = cvxjpeg::create(err);
+        if (!ctx->jpeg) return fail(ctx, CVX_ERR_UNSUPPORTED, "%s", err.c_str());
+    }
+    if (!ctx->presentStage) {
+        cudaError_t e = cudaMalloc(&ctx->presentStage, (size_t)W * H * 4);
+        if (e != cudaSuccess) return fail(ctx, e == cudaErrorMemoryAllocation ? CVX_ERR_OUT_OF_MEMORY : CVX_ERR_CUDA, "present staging allocation failed: %s", cudaGetErrorString(e));
+    }
+    CU(ctx, cvxd_launch_present_rgb8(current_target(ctx), (uint8_t*)ctx->presentStage, W, H, 1, ctx->stream));
+    ctx->launches++;
+    std::string err;
+    if (!cvxjpeg::encode(ctx->jpeg, (const uint8_t*)ctx->presentStage, W, H, quality, subsampling, ctx->stream, ctx->jpegOut, err))
+        return fail(ctx, CVX_ERR_CUDA, "%s", err.c_str());
+    *out_bytes = (int64_t)ctx->jpegOut.size();
+    if (dst_capacity == 0) return CVX_OK; // size query: the caller allocates and calls again
+    if ((int64_t)ctx->jpegOut.size() > dst_capacity)
+        return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "JPEG bitstream is %lld bytes, the destination holds %lld", (long long)ctx->jpegOut.size(), (long long)dst_capacity);
+    memcpy(dst, ctx->jpegOut.data(), ctx->jpegOut.size());
     return CVX_OK;
 }
 

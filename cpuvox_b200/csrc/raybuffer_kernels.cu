@@ -1307,6 +1307,30 @@ present_kernel(const uint32_t* __restrict__ frame, uint32_t* __restrict__ out, i
     }
 }
 
+// ColorARGB32 frame -> packed R,G,B bytes (3 per pixel: the input of still/video encoders and of image files), optionally top-down.
+// A thread takes 4 pixels (one 128-bit load) and writes 12 bytes as three words when the row pitch allows, else byte by byte.
+__global__ void __launch_bounds__(256)
+present_rgb8_kernel(const uint32_t* __restrict__ frame, uint8_t* __restrict__ out, int width, int height, int topDown) {
+    const int quadsPerRow = (width + 3) >> 2;
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (int64_t)quadsPerRow * height) return;
+    const int y = (int)(q / quadsPerRow), x = (int)(q - (int64_t)y * quadsPerRow) * 4;
+    const uint32_t* src = frame + (int64_t)y * width + x;
+    uint8_t* dst = out + ((int64_t)(topDown ? height - 1 - y : y) * width + x) * 3;
+    if ((width & 3) == 0) { // rows of 3 * width bytes start on a word boundary, and so does every quad
+        const uint4 v = *reinterpret_cast<const uint4*>(src);
+        uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+        d[0] = __byte_perm(v.x, v.y, 0x5321u); // r0 g0 b0 r1   (a pixel's bytes in memory: a, r, g, b)
+        d[1] = __byte_perm(v.y, v.z, 0x6532u); // g1 b1 r2 g2
+        d[2] = __byte_perm(v.z, v.w, 0x7653u); // b2 r3 g3 b3
+    } else {
+        for (int i = 0; i < 4 && x + i < width; i++) {
+            const uint32_t p = src[i];
+            dst[3 * i] = (uint8_t)(p >> 8); dst[3 * i + 1] = (uint8_t)(p >> 16); dst[3 * i + 2] = (uint8_t)(p >> 24);
+        }
+    }
+}
+
 __global__ void ray_setup_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ cvxd_frame f, cvxd_ray_state* out, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1395,6 +1419,12 @@ cudaError_t cvxd_launch_present(const uint32_t* frame, uint32_t* out, int width,
     if (width <= 0 || height <= 0) return cudaSuccess;
     const int64_t quads = (int64_t)((width + 3) >> 2) * height;
     present_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, stream>>>(frame, out, width, height, bgra, top_down);
+    return cudaGetLastError();
+}
+cudaError_t cvxd_launch_present_rgb8(const uint32_t* frame, uint8_t* out, int width, int height, int top_down, cudaStream_t stream) {
+    if (width <= 0 || height <= 0) return cudaSuccess;
+    const int64_t quads = (int64_t)((width + 3) >> 2) * height;
+    present_rgb8_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, stream>>>(frame, out, width, height, top_down);
     return cudaGetLastError();
 }
 #endif /* !CVX_EMU */

@@ -320,11 +320,19 @@ class RenderManager:
         self._ck(lib.cvx_blit_raybuffer(self._ctx, which))
 
     def present(self, fmt: int = 0, top_down: bool = True, out: Optional[np.ndarray] = None) -> np.ndarray:
-        """cvx_present to host memory: the frame as RGBA8 (fmt 0) or BGRA8 (fmt 1) bytes, rows top-down or bottom-up."""
+        """cvx_present to host memory: the frame as RGBA8 (fmt 0), BGRA8 (fmt 1) or packed RGB8 (fmt 2) bytes, rows top-down or bottom-up."""
         if out is None:
-            out = np.empty((self.height, self.width, 4), dtype=np.uint8)
+            out = np.empty((self.height, self.width, 3 if fmt == 2 else 4), dtype=np.uint8)
         self._ck(lib.cvx_present(self._ctx, fmt, int(top_down), _ptr(out), 0))
         return out
+
+    def present_jpeg(self, quality: int = 90, subsampling: int = 0) -> bytes:
+        """cvx_present_jpeg: the frame encoded on the device as a baseline JPEG (subsampling 0 = 4:4:4, 1 = 4:2:0); returns the bitstream."""
+        n = C.c_int64(0)
+        cap = self.width * self.height * 3 + 65536  # an upper bound no baseline JPEG of the frame exceeds in practice
+        buf = np.empty(cap, dtype=np.uint8)
+        self._ck(lib.cvx_present_jpeg(self._ctx, quality, subsampling, _ptr(buf), cap, C.byref(n)))
+        return buf[: n.value].tobytes()
 
     def present_device(self, device_ptr: int, fmt: int = 0, top_down: bool = True):
         """cvx_present into a caller-owned W*H*4 device buffer (graphics interop resource, encoder surface), on the context's stream."""

@@ -128,6 +128,7 @@ SYMBOLS = {
     "cvx_clear_raybuffers": (C.c_int, [_P, _U32]),
     "cvx_blit_raybuffer": (C.c_int, [_P, _I32]),
     "cvx_present": (C.c_int, [_P, _I32, _I32, _P, _I32]),
+    "cvx_present_jpeg": (C.c_int, [_P, _I32, _I32, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "cvx_alloc_pinned": (C.c_int, [_I64, C.POINTER(_P)]),
     "cvx_free_pinned": (C.c_int, [_P]),
     "cvx_device_frame": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_I64)]),

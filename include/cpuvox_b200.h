@@ -33,7 +33,8 @@ typedef enum cvx_status {
     CVX_ERR_NO_WORLD = -5,
     CVX_ERR_NO_RESOLUTION = -6,
     CVX_ERR_IO = -7,
-    CVX_ERR_FORMAT = -8
+    CVX_ERR_FORMAT = -8,
+    CVX_ERR_UNSUPPORTED = -9
 } cvx_status;
 
 /* ---- blittable per-frame inputs -------------------------------------------------------- */
@@ -142,13 +143,23 @@ int cvx_clear_raybuffers(cvx_ctx* ctx, uint32_t argb);
  * view into the framebuffer, stretched over the screen — screen x selects the ray row, screen y the pixel along the row, point
  * sampled. Use with cvx_clear_raybuffers(magenta) before the draw to see which pixels a frame wrote. */
 int cvx_blit_raybuffer(cvx_ctx* ctx, int32_t which);
-/* Presentation, the step after the path (replaces Unity's camera target): convert the framebuffer (ColorARGB32, row 0 = bottom) on
- * the device to RGBA8 or BGRA8 bytes, rows top-down (top_down != 0: what swap chains, image files and encoders take) or bottom-up,
- * into `dst`: a W*H*4 device buffer (dst_is_device != 0; e.g. a mapped graphics-interop resource or an encoder surface; ordered on
- * the context's stream) or host memory (the call returns when the copy has landed). */
+/* Presentation, the step after the path (replaces Unity's camera target, RenderManager.cs:192-193): convert the framebuffer
+ * (ColorARGB32, row 0 = bottom) on the device to RGBA8 / BGRA8 (4 bytes per pixel) or packed RGB8 (3 bytes per pixel), rows
+ * top-down (top_down != 0: what swap chains, image files and encoders take) or bottom-up, into `dst`: a device buffer of W*H*4
+ * (W*H*3 for RGB8) bytes (dst_is_device != 0; e.g. a mapped graphics-interop resource or an encoder surface; ordered on the
+ * context's stream) or host memory (the call returns when the copy has landed). */
 #define CVX_PRESENT_RGBA8 0
 #define CVX_PRESENT_BGRA8 1
+#define CVX_PRESENT_RGB8 2
 int cvx_present(cvx_ctx* ctx, int32_t format, int32_t top_down, void* dst, int32_t dst_is_device);
+/* Presentation as a compressed still: the framebuffer is packed to top-down RGB8 and encoded as a baseline JPEG ON THE DEVICE
+ * (nvJPEG's CUDA encoder, a CUDA toolkit library loaded with dlopen at the first call; CVX_ERR_UNSUPPORTED when it is not installed —
+ * nothing else in the library depends on it). Only the bitstream crosses to the host: *out_bytes receives its length, and it is
+ * copied to `dst` if dst_capacity holds it. dst_capacity == 0 queries the length (the frame is encoded, nothing is copied).
+ * quality 1..100; subsampling CVX_JPEG_444 (no chroma subsampling: hard voxel edges stay sharp) or CVX_JPEG_420. */
+#define CVX_JPEG_444 0
+#define CVX_JPEG_420 1
+int cvx_present_jpeg(cvx_ctx* ctx, int32_t quality, int32_t subsampling, void* dst, int64_t dst_capacity, int64_t* out_bytes);
 /* Page-locked host memory for asynchronous frame readback (cvx_draw_batch, cvx_read_frame). */
 int cvx_alloc_pinned(int64_t bytes, void** out);
 int cvx_free_pinned(void* p);

@@ -288,6 +288,17 @@ def test_draw_batch_equals_individual_draws(cv, rm, mill_world):
             assert np.array_equal(dst[i], f), (k, i)
         rm.draw_batch(setups)
         assert np.array_equal(rm.read_frame(), singles[-1]), k
+    # a batch much longer than the views in flight
+    many = [setups[(7 * i) % len(setups)] for i in range(37)]
+    big = cv.alloc_pinned((len(many), H, W))
+    for k in (2, 6):
+        rm.set_frames_in_flight(k)
+        big[:] = 0
+        rm.draw_batch(many, big)
+        for i in range(len(many)):
+            assert np.array_equal(big[i], singles[(7 * i) % len(setups)]), (k, i)
+        rm.draw_batch(many)
+        assert np.array_equal(rm.read_frame(), singles[(7 * 36) % len(setups)]), k
     rm.set_frames_in_flight(4)
     with pytest.raises(cv.CvxError):
         rm.set_frames_in_flight(9)
@@ -408,6 +419,8 @@ def test_debug_views_and_presentation(cv, orc, rm, mill_world, tmp_path):
         assert np.array_equal(rm.present(0, top_down=True), rgba[::-1])
         assert np.array_equal(rm.present(1, top_down=True), bgra[::-1])
         assert np.array_equal(rm.present(1, top_down=False), bgra)
+        assert np.array_equal(rm.present(2, top_down=True), rgba[::-1, :, :3])    # packed RGB8: word path at W % 4 == 0, byte path else
+        assert np.array_equal(rm.present(2, top_down=False), rgba[:, :, :3])
     # device destination: a torch buffer stands in for a mapped graphics resource
     import torch
     dst = torch.zeros(H * W, dtype=torch.int32, device="cuda:0")
@@ -418,6 +431,33 @@ def test_debug_views_and_presentation(cv, orc, rm, mill_world, tmp_path):
         rm.present(7)
     with pytest.raises(cv.CvxError):
         rm.blit_raybuffer(2)
+
+
+def test_present_jpeg_decodes_to_the_frame(cv, rm, mill_world):
+    """f4, encode of the device framebuffer: cvx_present_jpeg (frame -> RGB8 on the device -> nvJPEG CUDA encoder) must decode, with an
+    independent decoder (Pillow), to the frame within JPEG's loss: PSNR > 38 dB at quality 95 4:4:4, > 30 dB at quality 75 4:2:0, and the
+    bitstream must be much smaller than the frame. Odd sizes included (partial MCUs, the byte path of the RGB8 packer)."""
+    import io
+    from PIL import Image
+    rm.upload_world(mill_world)
+    for (W, H) in ((1280, 720), (333, 217)):
+        rm.set_resolution(W, H)
+        rm.draw_setup(rm.make_setup(pose_for(cv, mill_world, POSES[1])))
+        rm.sync()
+        want = rm.present(2, top_down=True).astype(np.float64)
+        for quality, sub, floor_db in ((95, 0, 38.0), (75, 1, 30.0)):
+            data = rm.present_jpeg(quality, sub)
+            assert data[:2] == b"\xff\xd8" and data[-2:] == b"\xff\xd9"
+            assert len(data) < W * H * 3 // 3
+            img = Image.open(io.BytesIO(data))
+            assert img.size == (W, H) and img.mode == "RGB"
+            got = np.asarray(img).astype(np.float64)
+            psnr = 10.0 * np.log10(255.0 ** 2 / max(1e-9, ((got - want) ** 2).mean()))
+            assert psnr > floor_db, (W, H, quality, sub, psnr)
+    with pytest.raises(cv.CvxError):
+        rm.present_jpeg(0)
+    with pytest.raises(cv.CvxError):
+        rm.present_jpeg(90, 5)
 
 
 def test_gpu_world_builder_matches_host_builder(cv, rm):
