@@ -72,7 +72,8 @@ public static unsafe class CpuVoxB200
 	[DllImport(LIB)] public static extern int cvx_builder_lod(IntPtr builder, int lod, out IntPtr blob, out long bytes, out int columnCount, out long voxelCount);
 	[DllImport(LIB)] public static extern void cvx_builder_free(IntPtr builder);
 	[DllImport(LIB)] public static extern int cvx_blit_raybuffer(IntPtr ctx, int which); // ERenderMode.RayBufferTopDown (0) / RayBufferLeftRight (1), UnityManager.cs:471-483
-	[DllImport(LIB)] public static extern int cvx_present(IntPtr ctx, int format, int topDown, void* dst, int dstIsDevice); // 0 = RGBA8, 1 = BGRA8
+	[DllImport(LIB)] public static extern int cvx_present(IntPtr ctx, int format, int topDown, void* dst, int dstIsDevice); // 0 = RGBA8, 1 = BGRA8, 2 = packed RGB8
+	[DllImport(LIB)] public static extern int cvx_present_jpeg(IntPtr ctx, int quality, int subsampling, void* dst, long dstCapacity, out long outBytes); // 0 = 4:4:4, 1 = 4:2:0; dstCapacity 0 = size query
 
 	public static void Check (int code, IntPtr ctx)
 	{

@@ -9,5 +9,5 @@ NV="/usr/local/cuda/bin/nvcc $* -DCVXD_MIN_CTAS_PER_SM=$minb -gencode arch=compu
 $NV -c -o /tmp/cvxvar_$name/k.o raybuffer_kernels.cu
 $NV -c -o /tmp/cvxvar_$name/c.o capi.cu
 [ -f host_setup.o ] || make -s
-/usr/local/cuda/bin/nvcc -shared -o ../variants/lib_$name.so /tmp/cvxvar_$name/k.o /tmp/cvxvar_$name/c.o world_builder_gpu.o host_setup.o world_builder.o -Xcompiler -pthread -cudart static -ldl
+/usr/local/cuda/bin/nvcc -shared -o ../variants/lib_$name.so /tmp/cvxvar_$name/k.o /tmp/cvxvar_$name/c.o world_builder_gpu.o host_setup.o world_builder.o jpeg_encoder.o -Xcompiler -pthread -cudart static -ldl
 echo built ../variants/lib_$name.so
