@@ -67,8 +67,8 @@ def parse_args():
     ap.add_argument("--res", default=None, help="WxH; default: the config's resolution (config 1: 3840x2160)")
     ap.add_argument("--maxdim", type=int, default=1024)
     ap.add_argument("--group", type=int, default=0, help="Phase-1 lanes per ray (0 = library default)")
-    ap.add_argument("--inflight", type=int, default=6, help="views in flight per cvx_draw_batch (1..8)")
-    ap.add_argument("--inflight-e2e", type=int, default=8, help="views in flight for the e2e leg (frame copies occupy the slots longer)")
+    ap.add_argument("--inflight", type=int, default=6, help="views in flight per cvx_draw_batch (1..16)")
+    ap.add_argument("--inflight-e2e", type=int, default=6, help="views in flight for the e2e leg (frames leave through the library's framebuffer pool: a slot does not wait for its copy)")
     ap.add_argument("--ring-slots", type=int, default=8, help="framebuffers of the gather ring (--mode rays)")
     ap.add_argument("--shard-chunk", type=int, default=512, help="--mode rays: rays are dealt to the ranks in chunks of this many (power of two)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -585,7 +585,7 @@ def run_b200(a, rank, local_rank, world_size):
                 at_inflight[str(k)] = {"value": nviews * max(2, a.steps // 3) * world_size / (float(t.item()) / 1000.0), "unit": "frames/s"}
         rm.set_frames_in_flight(a.inflight)
         pinned = cv.alloc_pinned((nviews, h, w))
-        rm.set_frames_in_flight(a.inflight_e2e)   # a slot is busy with its device->host copy too: more slots keep the GPU fed
+        rm.set_frames_in_flight(a.inflight_e2e)   # frames leave through the framebuffer pool (cvx_draw_batch): the slots do not wait for the copies
         e2e_s = time_e2e(torch, dist, cv, rm, poses, steps, a.warmup, device, world_size, pinned)
         rm.set_frames_in_flight(a.inflight)
         N.lib.cvx_free_pinned(pinned.ctypes.data)

@@ -25,8 +25,9 @@ static_assert(sizeof(cvx_ray_state) == sizeof(cvxd_ray_state), "ray state layout
 static_assert(sizeof(cvx_counters) == sizeof(cvxd_counters), "counter layout");
 static_assert(CVX_LOD_LEVELS == CVXD_LODS, "lod levels");
 
-#define CVX_MAX_SLOTS 8
+#define CVX_MAX_SLOTS 16
 #define CVX_DEFAULT_SLOTS 6
+#define CVX_POOL_FRAMES 32 /* cvx_draw_batch with a host destination: framebuffers between Phase 2 and the device->host copies */
 
 extern "C" int cvx_ring_close(cvx_ctx* ctx);
 
@@ -60,6 +61,11 @@ struct cvx_ctx {
     int extraReady = 0;                 // extra slots holding buffers for the current resolution
     int lastSlot = 0;                   // slot of the most recent view (what the read functions return)
     cudaEvent_t evBatchStart = nullptr;
+    // cvx_draw_batch with dst_frames: Phase 2 writes into a pool of framebuffers that a copy stream drains, so a slot starts its next
+    // view without waiting for its frame's device->host copy (poolReady[p]: frame p rendered; poolFree[p]: frame p copied out)
+    uint32_t* pool[CVX_POOL_FRAMES] = {nullptr};
+    cudaEvent_t poolReady[CVX_POOL_FRAMES] = {nullptr}, poolFree[CVX_POOL_FRAMES] = {nullptr};
+    int poolCount = 0;                  // pool frames allocated for the current resolution
     uint32_t* externalFrame = nullptr;
     uint32_t* presentStage = nullptr;   // cvx_present with a host destination / cvx_present_jpeg: converted frame (W*H*4 bytes)
     cvxjpeg::Encoder* jpeg = nullptr;   // created by the first cvx_present_jpeg
@@ -205,6 +211,25 @@ void free_extra_slots(cvx_ctx* ctx) {
     }
     ctx->extraReady = 0;
     ctx->lastSlot = 0;
+    if (ctx->copyStream) cudaStreamSynchronize(ctx->copyStream);
+    for (int i = 0; i < CVX_POOL_FRAMES; i++) { cudaFree(ctx->pool[i]); ctx->pool[i] = nullptr; }
+    ctx->poolCount = 0;
+}
+
+// `want` pool framebuffers of the current resolution (events are created once per context)
+int ensure_pool(cvx_ctx* ctx, int want) {
+    if (want > CVX_POOL_FRAMES) want = CVX_POOL_FRAMES;
+    const size_t fbBytes = (size_t)ctx->width * ctx->height * 4;
+    while (ctx->poolCount < want) {
+        const int i = ctx->poolCount;
+        cudaError_t e = cudaSuccess;
+        if (!ctx->poolReady[i]) e = cudaEventCreateWithFlags(&ctx->poolReady[i], cudaEventDisableTiming);
+        if (e == cudaSuccess && !ctx->poolFree[i]) e = cudaEventCreateWithFlags(&ctx->poolFree[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->pool[i], fbBytes);
+        if (e != cudaSuccess) { ctx->pool[i] = nullptr; return fail(ctx, e == cudaErrorMemoryAllocation ? CVX_ERR_OUT_OF_MEMORY : CVX_ERR_CUDA, "frame pool allocation failed: %s", cudaGetErrorString(e)); }
+        ctx->poolCount++;
+    }
+    return CVX_OK;
 }
 
 // slots 1 .. want-1 get a stream, an event and zero-initialised buffers of the current resolution
@@ -344,6 +369,10 @@ int cvx_destroy(cvx_ctx* ctx) {
     for (int i = 0; i < 2; i++) {
         if (ctx->evFrameDone[i]) cudaEventDestroy(ctx->evFrameDone[i]);
         if (ctx->evCopyDone[i]) cudaEventDestroy(ctx->evCopyDone[i]);
+    }
+    for (int i = 0; i < CVX_POOL_FRAMES; i++) {
+        if (ctx->poolReady[i]) cudaEventDestroy(ctx->poolReady[i]);
+        if (ctx->poolFree[i]) cudaEventDestroy(ctx->poolFree[i]);
     }
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
@@ -522,22 +551,48 @@ int cvx_draw_batch(cvx_ctx* ctx, const cvx_frame_setup* setups, int32_t n_views,
     if (n_views == 0) return CVX_OK;
     CU(ctx, cudaSetDevice(ctx->device));
     const size_t fbBytes = (size_t)ctx->width * ctx->height * 4;
-    // View i renders on slot i % K: Phase 1, Phase 2 and (with dst_frames) the device->host copy of its frame are stream-ordered
-    // inside the slot, and the K slots overlap each other — the long tail of one view's few heavy rays runs beside the bulk of
-    // the next views, and frame copies run beside kernels. A caller-owned external frame forces one slot (one target buffer).
+    // View i renders on slot i % K: Phase 1 and Phase 2 are stream-ordered inside the slot and the K slots overlap each other — the
+    // long tail of one view's few heavy rays runs beside the bulk of the next views. With dst_frames, Phase 2 writes into a pool of
+    // framebuffers which the copy stream drains in view order: the slot goes on to its next view at once, and the device->host
+    // copies (0.6 ms per 4K frame, most of the copy engine's time at the rate the kernels deliver) never hold a slot back. The last
+    // view renders into its slot's own framebuffer, so the read functions and device pointers refer to it after the call.
+    // A caller-owned external frame forces one slot (one target buffer).
     const int K = ctx->externalFrame ? 1 : (ctx->slotCount < n_views ? ctx->slotCount : n_views);
     for (int i = 0; i < n_views; i++)  // every view is checked before the first one is enqueued
         if ((r = validate_setup(ctx, setups + i, 0))) return r;
     if ((r = ensure_slots(ctx, K))) return r;
+    const bool pooled = dst_frames && !ctx->externalFrame && n_views > 1;
+    const int M = CVX_POOL_FRAMES < n_views - 1 ? CVX_POOL_FRAMES : n_views - 1;
+    if (pooled && (r = ensure_pool(ctx, M))) return r;
     CU(ctx, cudaEventRecord(ctx->evBatchStart, ctx->stream)); // the slots start after everything queued on the context's stream
     for (int s = 1; s < K; s++) CU(ctx, cudaStreamWaitEvent(slot_stream(ctx, s), ctx->evBatchStart, 0));
     cudaError_t ce = cudaSuccess;
     for (int i = 0; i < n_views && !r && ce == cudaSuccess; i++) {
         const int slot = i % K;
+        cudaStream_t st = slot_stream(ctx, slot);
+        if (pooled) {
+            const bool last = i == n_views - 1;
+            const int pf = i % M;
+            uint32_t* target = last ? slot_frame(ctx, slot) : ctx->pool[pf];
+            if (!last && i >= M) ce = cudaStreamWaitEvent(st, ctx->poolFree[pf], 0);   // the copy of view i - M has left the buffer
+            if (ce == cudaSuccess) r = draw_into(ctx, setups + i, slot, target, false);
+            if (r || ce != cudaSuccess) break;
+            cudaEvent_t ready = last ? ctx->evFrameDone[0] : ctx->poolReady[pf];
+            ce = cudaEventRecord(ready, st);
+            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->copyStream, ready, 0);
+            // the copy is asynchronous only if dst_frames is page-locked (cvx_alloc_pinned / cudaHostRegister)
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync((uint8_t*)dst_frames + (size_t)i * fbBytes, target, fbBytes, cudaMemcpyDeviceToHost, ctx->copyStream);
+            if (ce == cudaSuccess && !last) ce = cudaEventRecord(ctx->poolFree[pf], ctx->copyStream);
+            continue;
+        }
         uint32_t* target = ctx->externalFrame ? ctx->externalFrame : slot_frame(ctx, slot);
         r = draw_into(ctx, setups + i, slot, target, false);
-        // the copy is asynchronous only if dst_frames is page-locked (cvx_alloc_pinned / cudaHostRegister)
-        if (!r && dst_frames) ce = cudaMemcpyAsync((uint8_t*)dst_frames + (size_t)i * fbBytes, target, fbBytes, cudaMemcpyDeviceToHost, slot_stream(ctx, slot));
+        if (!r && dst_frames) ce = cudaMemcpyAsync((uint8_t*)dst_frames + (size_t)i * fbBytes, target, fbBytes, cudaMemcpyDeviceToHost, st);
+    }
+    if (pooled) {   // the context's stream also waits for the copies
+        cudaError_t e1 = cudaEventRecord(ctx->evCopyDone[0], ctx->copyStream);
+        if (e1 == cudaSuccess) e1 = cudaStreamWaitEvent(ctx->stream, ctx->evCopyDone[0], 0);
+        if (ce == cudaSuccess) ce = e1;
     }
     // join — also after a failure in the middle of the batch, so that the slots' work stays ordered before whatever the caller
     // queues next on the context's stream (events, reads, the next batch)
@@ -1013,6 +1068,9 @@ int cvx_draw_sharded(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t ray_beg
     }
     f.ray_begin = ray_begin; f.ray_end = ray_end;
     ring_flags* fl = ring_flag_block(ctx, rslot);
+    const bool prof = ctx->profCount < ctx->profCapacity;   // cvx_profile_begin: events around this share's Phase 1 and Phase 2
+    cudaEvent_t* pe = prof ? &ctx->profEvents[3 * (size_t)ctx->profCount] : nullptr;
+    if (prof) CU(ctx, cudaEventRecord(pe[0], stream));
     CU(ctx, cvxd_launch_phase1(ctx->world, f, ctx->groupSize, stream));   // Phase 1 writes this rank's own raybuffers: no need to wait for the ring
     if (ray_end > ray_begin) ctx->launches++;
     if (view_index >= ctx->ringSlots) {  // the ring frame still holds view_index - slots until the root releases it
@@ -1024,7 +1082,9 @@ int cvx_draw_sharded(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t ray_beg
     b.td = f.td; b.lr = f.lr;
     b.ray_begin = ray_begin; b.ray_end = ray_end; b.owned_only = 1;
     b.il_chunk = f.il_chunk; b.il_ranks = f.il_ranks; b.il_rank = f.il_rank;
+    if (prof) CU(ctx, cudaEventRecord(pe[1], stream));
     CU(ctx, cvxd_launch_phase2(b, stream));
+    if (prof) { CU(ctx, cudaEventRecord(pe[2], stream)); ctx->profCount++; }
     ring_signal_kernel<<<1, 1, 0, stream>>>(&fl->arrive[rank], (uint32_t)(view_index + 1));
     ctx->launches += 2;
     CU(ctx, cudaGetLastError());

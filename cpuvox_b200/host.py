@@ -359,7 +359,7 @@ class RenderManager:
         self.set_option(N.OPT_COUNTERS, int(on))
 
     def set_frames_in_flight(self, k: int):
-        """Views of one draw_batch rendered concurrently (1..8, default 6), each on its own stream and buffer set."""
+        """Views of one draw_batch rendered concurrently (1..16, default 6), each on its own stream and buffer set."""
         self.set_option(N.OPT_FRAMES_IN_FLIGHT, k)
 
     def set_general_path(self, on: bool):

@@ -123,8 +123,10 @@ int cvx_blit_rows(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t row_begin,
 int cvx_blit_owned(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t ray_begin, int32_t ray_end, void* device_frame);
 /* Batched views over one world: n frames, up to CVX_OPT_FRAMES_IN_FLIGHT of them in flight at
  * once; frame i is read back (if dst_frames != NULL) to dst_frames + i*W*H*4 and the call returns when all frames are on the
- * host. With dst_frames == NULL the call only enqueues: the frames stay on the device (the read functions and device
- * pointers refer to the LAST view), ordered before anything queued later on the context's stream. */
+ * host. With dst_frames == NULL the call only enqueues: the frames stay on the device, ordered before anything queued later on
+ * the context's stream. Either way the read functions and device pointers refer to the LAST view afterwards.
+ * With dst_frames the frames pass through a pool of up to 32 device framebuffers (allocated on first use, W*H*4 bytes each) that
+ * a copy stream drains in view order, so rendering runs ahead of the device->host copies instead of waiting for them. */
 int cvx_draw_batch(cvx_ctx* ctx, const cvx_frame_setup* setups, int32_t n_views, void* dst_frames);
 int cvx_sync(cvx_ctx* ctx);
 
@@ -179,7 +181,7 @@ int64_t cvx_launch_count(const cvx_ctx* ctx);
  *   CVX_OPT_COUNTERS    1 = accumulate cvx_counters (same as CVX_FLAG_COUNTERS at creation), 0 = off.
  *   CVX_OPT_GENERAL_PATH 1 = always run the general Phase-1 kernel (reads the reference element area run by run); 0 (default) =
  *                       use the boundary-table kernel whenever the uploaded world is regular (see cvx_world_is_regular).
- *   CVX_OPT_FRAMES_IN_FLIGHT 1..8 (default 6): views of one cvx_draw_batch rendered concurrently, each on its own stream with its
+ *   CVX_OPT_FRAMES_IN_FLIGHT 1..16 (default 6): views of one cvx_draw_batch rendered concurrently, each on its own stream with its
  *                       own raybuffers and framebuffer (the reference double-buffers its raybuffers for the same reason,
  *                       RenderManager.cs:14,53-56). Extra buffer sets are allocated on the first batch that needs them. */
 #define CVX_OPT_GROUP_SIZE 1

@@ -297,11 +297,12 @@ def test_draw_batch_equals_individual_draws(cv, rm, mill_world):
         rm.draw_batch(many, big)
         for i in range(len(many)):
             assert np.array_equal(big[i], singles[(7 * i) % len(setups)]), (k, i)
+        assert np.array_equal(rm.read_frame(), singles[(7 * 36) % len(setups)]), k   # the last view also stays readable on the device
         rm.draw_batch(many)
         assert np.array_equal(rm.read_frame(), singles[(7 * 36) % len(setups)]), k
     rm.set_frames_in_flight(4)
     with pytest.raises(cv.CvxError):
-        rm.set_frames_in_flight(9)
+        rm.set_frames_in_flight(17)
 
 
 def test_draw_world_batch_equals_setup_batch(cv, rm, mill_world):
