@@ -215,3 +215,8 @@ def random_world_and_cameras(cv, rng, cameras=4):
         euler = (float(rng.uniform(-89.5, 89.5)), float(rng.uniform(0, 360)), float(rng.choice([0.0, 0.0, rng.uniform(-180, 180)])))
         poses.append(cv.CameraPose.from_euler(pos, euler, far_clip=float(rng.uniform(10, 4 * max(dx, dy, dz)))))
     return world, blob, cc, W, H, poses
+
+
+def partition_rays_even(total: int, ranks: int, rank: int):
+    """Contiguous, equally sized ray ranges (test helper for the sharded draws)."""
+    return total * rank // ranks, total * (rank + 1) // ranks

@@ -262,6 +262,41 @@ def test_ray_ranges_blit_rows_and_owned_blits_compose(cv, rm, terrain_world):
     assert np.array_equal(acc.astype(np.uint32), frame)
 
 
+def test_frame_ring_shares_compose_on_one_device(cv, rm, terrain_world, mill_world):
+    """The ray-sharded path of SURVEY.md §8(e) without a second GPU: a frame ring for N ranks lives in this process, every rank's share
+    of a view (cvx_draw_sharded: Phase 1 of its rays, Phase 2 of the pixels they feed — strips of tiles, most of them skipped) is stored
+    into the same ring frame, and the consumed frame must equal the single-launch frame bit for bit: interleaved chunks and contiguous
+    ranges, 2 / 3 / 8 ranks, widths that end inside a tile and inside a strip of tiles."""
+    from conftest import partition_rays_even
+    for world, W, H in ((terrain_world, 1000, 600), (mill_world, 1920, 1080), (terrain_world, 333, 217)):
+        rm.upload_world(world)
+        rm.set_resolution(W, H)
+        rm.set_frames_in_flight(1)
+        out = cv.alloc_pinned((1, H, W))
+        view = 0
+        for spec in (POSES[0], POSES[3], POSES[8]):
+            s = rm.make_setup(pose_for(cv, world, spec))
+            rm.draw_setup(s)
+            rm.sync()
+            want = rm.read_frame().copy()
+            total = sum(max(0, s.segments[k].ray_count) for k in range(4))
+            for n, chunk in ((2, 32), (3, 0), (8, 512), (8, 64)):
+                rm.ring_create(4, n)
+                out[:] = 0
+                for r in range(n):
+                    if chunk:
+                        rm.draw_sharded(s, -1, chunk, view, r)
+                    else:
+                        b, e = partition_rays_even(total, n, r)
+                        rm.draw_sharded(s, b, e, view, r)
+                rm.ring_consume(view, out[0])
+                rm.sync()
+                rm.ring_status()
+                assert np.array_equal(out[0], want), (W, H, spec[0], n, chunk)
+                rm.ring_close()
+    rm.set_frames_in_flight(6)
+
+
 def test_draw_batch_equals_individual_draws(cv, rm, mill_world):
     world = mill_world
     rm.upload_world(world)
