@@ -17,9 +17,10 @@ value    frames/s with everything resident in HBM: per frame one Phase-1 and one
          cvx_draw_batch over the views (device only), which keeps up to `frames_in_flight` views in flight, each on its own
          stream with its own raybuffers and framebuffer (the reference double-buffers its raybuffers for the same overlap,
          RenderManager.cs:14,53-56). "at_inflight" repeats the measurement with 1 and 2 views in flight (the interactive case).
-e2e      frames/s through the public C ABI with HOST buffers (cvx_draw_world_batch = RenderManager.DrawWorld per camera): per
+e2e      frames/s through the public C ABI with HOST buffers (cvx_draw_world_batch_async = RenderManager.DrawWorld per camera): per
          frame the host computes the segment/VP setup from the camera pose, passes it by value (kernel parameters are the only
-         host->device bytes) and receives the finished frame in pinned host memory (copy overlapped with the next frames' kernels).
+         host->device bytes) and receives the finished frame in pinned host memory (copies overlapped with the next frames' kernels;
+         two pinned destinations, the host waits for step k - 1 while step k renders; --e2e-sync: one synchronous call per step).
          "d2h_ceiling" is a probe of the box: every rank copying framebuffer-sized pinned blocks at the same time, nothing else running.
 roofline Phase-1 kernel (dominant): algorithmic bytes of SURVEY.md §8(d) per launch / launch duration against the measured
          HBM copy bandwidth of MEASURED_PEAKS.json. Launches of different views overlap, so the duration used is the timed
@@ -71,6 +72,7 @@ def parse_args():
     ap.add_argument("--inflight-e2e", type=int, default=6, help="views in flight for the e2e leg (frames leave through the library's framebuffer pool: a slot does not wait for its copy)")
     ap.add_argument("--ring-slots", type=int, default=8, help="framebuffers of the gather ring (--mode rays)")
     ap.add_argument("--shard-chunk", type=int, default=512, help="--mode rays: rays are dealt to the ranks in chunks of this many (power of two)")
+    ap.add_argument("--e2e-sync", action="store_true", help="e2e leg through the synchronous cvx_draw_world_batch (one call per step, returns when its frames are on the host) instead of double-buffered asynchronous batches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-1080p", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip at_inflight, d2h_ceiling and rays_sharded (profiling runs)")
@@ -360,21 +362,33 @@ def time_path(torch, dist, rm, setups, steps, warmup, device, flush, world_size,
     return ms, p1, p2, n, rm.launch_count() - launches0, (t0, t1)
 
 
-def time_e2e(torch, dist, cv, rm, poses, steps, warmup, device, world_size, pinned):
-    """Public-API path with host buffers: host setup per frame, frames delivered to pinned host memory."""
-    def one_step():
+def time_e2e(torch, dist, cv, rm, poses, steps, warmup, device, world_size, pinned, sync_calls=False):
+    """Public-API path with host buffers: host setup per frame, frames delivered to pinned host memory. `pinned` holds two destinations:
+    step k goes into pinned[k % 2] through cvx_draw_world_batch_async and the host waits for step k - 1 while step k renders (a consumer
+    that double-buffers its frames; every frame's copy lies inside the timed region, which ends when the last step's frames have landed).
+    sync_calls: the synchronous cvx_draw_world_batch per step instead (returns when the step's frames are on the host)."""
+    def run(n):
         # RenderManager.DrawWorld per camera: the host part (LimitRotationHorizon, vanishing point, segments, CameraData) is computed
-        # inside the call from the poses; kernels + device->host frame copies; returns when all frames are on the host
-        rm.draw_world_batch(poses, pinned)
+        # inside the call from the poses; kernels + device->host frame copies
+        prev = None
+        batch = rm.pose_batch(poses)    # marshalled once (the poses of a step are the same every step)
+        for k in range(n):
+            if sync_calls:
+                rm.draw_world_batch(poses, pinned[k % 2])
+                continue
+            cur = rm.draw_world_batch_async(batch, pinned[k % 2])
+            if prev is not None:
+                rm.batch_wait(prev)      # the frames of step k - 1 are on the host; its buffer is free for step k + 1
+            prev = cur
+        if prev is not None:
+            rm.batch_wait(prev)
 
-    for _ in range(max(1, warmup // 2)):
-        one_step()
+    run(max(2, warmup // 2))
     torch.cuda.synchronize(device)
     if world_size > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        one_step()
+    run(steps)
     torch.cuda.synchronize(device)
     dt = time.perf_counter() - t0
     if world_size > 1:
@@ -584,9 +598,9 @@ def run_b200(a, rank, local_rank, world_size):
                     dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 at_inflight[str(k)] = {"value": nviews * max(2, a.steps // 3) * world_size / (float(t.item()) / 1000.0), "unit": "frames/s"}
         rm.set_frames_in_flight(a.inflight)
-        pinned = cv.alloc_pinned((nviews, h, w))
+        pinned = cv.alloc_pinned((2, nviews, h, w))
         rm.set_frames_in_flight(a.inflight_e2e)   # frames leave through the framebuffer pool (cvx_draw_batch): the slots do not wait for the copies
-        e2e_s = time_e2e(torch, dist, cv, rm, poses, steps, a.warmup, device, world_size, pinned)
+        e2e_s = time_e2e(torch, dist, cv, rm, poses, steps, a.warmup, device, world_size, pinned, sync_calls=a.e2e_sync)
         rm.set_frames_in_flight(a.inflight)
         N.lib.cvx_free_pinned(pinned.ctypes.data)
         t = torch.tensor([ms, e2e_s * 1000.0, p1, p2, x1, x2], dtype=torch.float64, device=f"cuda:{device}")
@@ -687,7 +701,9 @@ def run_b200(a, rank, local_rank, world_size):
         },
         "e2e": {"value": e2e_fps, "unit": "frames/s",
                 "h2d_bytes_per_step": nviews * world_size * __import__("ctypes").sizeof(N.FrameSetup),
-                "d2h_bytes_per_step": nviews * world_size * W * H * 4},
+                "d2h_bytes_per_step": nviews * world_size * W * H * 4,
+                "call": "cvx_draw_world_batch (synchronous, one call per step)" if a.e2e_sync else
+                        "cvx_draw_world_batch_async + cvx_batch_wait, two pinned destinations: step k renders while step k - 1's frames finish landing"},
         "gpu_launches": main["launches"],
         "clocks": clocks,
     }

@@ -66,6 +66,10 @@ struct cvx_ctx {
     uint32_t* pool[CVX_POOL_FRAMES] = {nullptr};
     cudaEvent_t poolReady[CVX_POOL_FRAMES] = {nullptr}, poolFree[CVX_POOL_FRAMES] = {nullptr};
     int poolCount = 0;                  // pool frames allocated for the current resolution
+    bool poolUsed[CVX_POOL_FRAMES] = {false};
+    // asynchronous batches (cvx_draw_batch_async): batchDone[b % 4] is recorded on the copy stream behind batch b's last copy
+    cudaEvent_t batchDone[4] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t batchSeq = 0;
     uint32_t* externalFrame = nullptr;
     uint32_t* presentStage = nullptr;   // cvx_present with a host destination / cvx_present_jpeg: converted frame (W*H*4 bytes)
     cvxjpeg::Encoder* jpeg = nullptr;   // created by the first cvx_present_jpeg
@@ -212,7 +216,7 @@ void free_extra_slots(cvx_ctx* ctx) {
     ctx->extraReady = 0;
     ctx->lastSlot = 0;
     if (ctx->copyStream) cudaStreamSynchronize(ctx->copyStream);
-    for (int i = 0; i < CVX_POOL_FRAMES; i++) { cudaFree(ctx->pool[i]); ctx->pool[i] = nullptr; }
+    for (int i = 0; i < CVX_POOL_FRAMES; i++) { cudaFree(ctx->pool[i]); ctx->pool[i] = nullptr; ctx->poolUsed[i] = false; }
     ctx->poolCount = 0;
 }
 
@@ -370,6 +374,7 @@ int cvx_destroy(cvx_ctx* ctx) {
         if (ctx->evFrameDone[i]) cudaEventDestroy(ctx->evFrameDone[i]);
         if (ctx->evCopyDone[i]) cudaEventDestroy(ctx->evCopyDone[i]);
     }
+    for (int i = 0; i < 4; i++) if (ctx->batchDone[i]) cudaEventDestroy(ctx->batchDone[i]);
     for (int i = 0; i < CVX_POOL_FRAMES; i++) {
         if (ctx->poolReady[i]) cudaEventDestroy(ctx->poolReady[i]);
         if (ctx->poolFree[i]) cudaEventDestroy(ctx->poolFree[i]);
@@ -544,10 +549,13 @@ int cvx_draw(cvx_ctx* ctx, const cvx_frame_setup* setup) {
     return draw_into(ctx, setup, 0, current_target(ctx), true);
 }
 
-int cvx_draw_batch(cvx_ctx* ctx, const cvx_frame_setup* setups, int32_t n_views, void* dst_frames) {
+// out_batch == NULL: cvx_draw_batch (with dst_frames the call returns when the frames are on the host); else cvx_draw_batch_async
+static int draw_batch_impl(cvx_ctx* ctx, const cvx_frame_setup* setups, int32_t n_views, void* dst_frames, int64_t* out_batch) {
     int r = check_ready(ctx, setups);
     if (r) return r;
     if (n_views < 0) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "n_views < 0");
+    const bool async = out_batch != nullptr;
+    if (async && (!dst_frames || n_views < 2 || ctx->externalFrame)) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "an asynchronous batch needs a host destination, at least two views and no external frame");
     if (n_views == 0) return CVX_OK;
     CU(ctx, cudaSetDevice(ctx->device));
     const size_t fbBytes = (size_t)ctx->width * ctx->height * 4;
@@ -574,7 +582,10 @@ int cvx_draw_batch(cvx_ctx* ctx, const cvx_frame_setup* setups, int32_t n_views,
             const bool last = i == n_views - 1;
             const int pf = i % M;
             uint32_t* target = last ? slot_frame(ctx, slot) : ctx->pool[pf];
-            if (!last && i >= M) ce = cudaStreamWaitEvent(st, ctx->poolFree[pf], 0);   // the copy of view i - M has left the buffer
+            // the previous user of the buffer (view i - M, or a view of an earlier asynchronous batch) has been copied out; the last view's
+            // own framebuffer may still be read by the previous asynchronous batch's final copy
+            if (!last && ctx->poolUsed[pf]) ce = cudaStreamWaitEvent(st, ctx->poolFree[pf], 0);
+            if (last && ctx->batchSeq > 0) ce = cudaStreamWaitEvent(st, ctx->batchDone[(ctx->batchSeq - 1) % 4], 0);
             if (ce == cudaSuccess) r = draw_into(ctx, setups + i, slot, target, false);
             if (r || ce != cudaSuccess) break;
             cudaEvent_t ready = last ? ctx->evFrameDone[0] : ctx->poolReady[pf];
@@ -582,14 +593,20 @@ int cvx_draw_batch(cvx_ctx* ctx, const cvx_frame_setup* setups, int32_t n_views,
             if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->copyStream, ready, 0);
             // the copy is asynchronous only if dst_frames is page-locked (cvx_alloc_pinned / cudaHostRegister)
             if (ce == cudaSuccess) ce = cudaMemcpyAsync((uint8_t*)dst_frames + (size_t)i * fbBytes, target, fbBytes, cudaMemcpyDeviceToHost, ctx->copyStream);
-            if (ce == cudaSuccess && !last) ce = cudaEventRecord(ctx->poolFree[pf], ctx->copyStream);
+            if (ce == cudaSuccess && !last) { ce = cudaEventRecord(ctx->poolFree[pf], ctx->copyStream); ctx->poolUsed[pf] = true; }
             continue;
         }
         uint32_t* target = ctx->externalFrame ? ctx->externalFrame : slot_frame(ctx, slot);
         r = draw_into(ctx, setups + i, slot, target, false);
         if (!r && dst_frames) ce = cudaMemcpyAsync((uint8_t*)dst_frames + (size_t)i * fbBytes, target, fbBytes, cudaMemcpyDeviceToHost, st);
     }
-    if (pooled) {   // the context's stream also waits for the copies
+    if (pooled && async) {   // the copies of this batch are followed by its completion event; nothing waits for them here
+        if (!ctx->batchDone[ctx->batchSeq % 4]) {
+            cudaError_t e0 = cudaEventCreateWithFlags(&ctx->batchDone[ctx->batchSeq % 4], cudaEventDisableTiming);
+            if (ce == cudaSuccess) ce = e0;
+        }
+        if (ce == cudaSuccess) ce = cudaEventRecord(ctx->batchDone[ctx->batchSeq % 4], ctx->copyStream);
+    } else if (pooled) {     // the context's stream also waits for the copies
         cudaError_t e1 = cudaEventRecord(ctx->evCopyDone[0], ctx->copyStream);
         if (e1 == cudaSuccess) e1 = cudaStreamWaitEvent(ctx->stream, ctx->evCopyDone[0], 0);
         if (ce == cudaSuccess) ce = e1;
@@ -603,15 +620,38 @@ int cvx_draw_batch(cvx_ctx* ctx, const cvx_frame_setup* setups, int32_t n_views,
     }
     if (r) return r;
     CU(ctx, ce);
+    if (async) { *out_batch = ctx->batchSeq++; return CVX_OK; }
     if (dst_frames) CU(ctx, cudaStreamSynchronize(ctx->stream)); // frames are on the host when the call returns
+    return CVX_OK;
+}
+
+int cvx_draw_batch(cvx_ctx* ctx, const cvx_frame_setup* setups, int32_t n_views, void* dst_frames) {
+    return draw_batch_impl(ctx, setups, n_views, dst_frames, nullptr);
+}
+
+// The kernels of consecutive asynchronous batches follow each other on the same buffer sets while the copy stream is still delivering
+// the earlier batch's frames: the copy backlog at the end of a batch (the views of a batch can finish several times faster than one
+// copy engine drains them) overlaps the next batch's rendering instead of idling the GPU.
+int cvx_draw_batch_async(cvx_ctx* ctx, const cvx_frame_setup* setups, int32_t n_views, void* dst_frames, int64_t* out_batch) {
+    if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
+    if (!out_batch) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "out_batch is NULL");
+    return draw_batch_impl(ctx, setups, n_views, dst_frames, out_batch);
+}
+
+int cvx_batch_wait(cvx_ctx* ctx, int64_t batch) {
+    if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
+    if (batch < 0 || batch >= ctx->batchSeq) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "no such batch (%lld)", (long long)batch);
+    CU(ctx, cudaSetDevice(ctx->device));
+    // the events of older batches have been re-recorded behind newer ones on the same in-order copy stream: waiting for those covers them
+    CU(ctx, cudaEventSynchronize(ctx->batchDone[batch % 4]));
     return CVX_OK;
 }
 
 // RenderManager.DrawWorld for headless hosts (RenderManager.cs:111-194 with UnityManager.LateUpdate's LimitRotationHorizon, UnityManager.cs:181):
 // the per-frame host part (vanishing point, segments, CameraData) is computed here from each pose, then the views go through
 // cvx_draw_batch. One call per batch: no per-view crossing of the FFI boundary.
-int cvx_draw_world_batch(cvx_ctx* ctx, const cvx_pose* poses, int32_t n_views, const float lod_distances[CVX_LOD_LEVELS],
-                         int32_t limit_rotation_horizon, void* dst_frames) {
+static int world_batch_impl(cvx_ctx* ctx, const cvx_pose* poses, int32_t n_views, const float lod_distances[CVX_LOD_LEVELS],
+                            int32_t limit_rotation_horizon, void* dst_frames, int64_t* out_batch) {
     if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
     if (!poses || n_views < 1 || !lod_distances) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "bad pose batch");
     if (ctx->world.lod_count <= 0) return fail(ctx, CVX_ERR_NO_WORLD, "no world uploaded");
@@ -624,7 +664,19 @@ int cvx_draw_world_batch(cvx_ctx* ctx, const cvx_pose* poses, int32_t n_views, c
         int r = cvx_host_frame_setup(&p, lod_distances, ctx->world.dim_y, &setups[(size_t)i]);
         if (r) return fail(ctx, r, "frame setup of view %d failed", i);
     }
-    return cvx_draw_batch(ctx, setups.data(), n_views, dst_frames);
+    return draw_batch_impl(ctx, setups.data(), n_views, dst_frames, out_batch);   // kernel parameters are copied at launch: setups may go
+}
+
+int cvx_draw_world_batch(cvx_ctx* ctx, const cvx_pose* poses, int32_t n_views, const float lod_distances[CVX_LOD_LEVELS],
+                         int32_t limit_rotation_horizon, void* dst_frames) {
+    return world_batch_impl(ctx, poses, n_views, lod_distances, limit_rotation_horizon, dst_frames, nullptr);
+}
+
+int cvx_draw_world_batch_async(cvx_ctx* ctx, const cvx_pose* poses, int32_t n_views, const float lod_distances[CVX_LOD_LEVELS],
+                               int32_t limit_rotation_horizon, void* dst_frames, int64_t* out_batch) {
+    if (!ctx) return CVX_ERR_INVALID_ARGUMENT;
+    if (!out_batch) return fail(ctx, CVX_ERR_INVALID_ARGUMENT, "out_batch is NULL");
+    return world_batch_impl(ctx, poses, n_views, lod_distances, limit_rotation_horizon, dst_frames, out_batch);
 }
 
 int cvx_sync(cvx_ctx* ctx) {

@@ -293,6 +293,30 @@ class RenderManager:
         lods = (C.c_float * LOD_LEVELS)(*[float(x) for x in self.lod_distances])
         self._ck(lib.cvx_draw_world_batch(self._ctx, arr, len(poses), C.byref(lods), int(limit_horizon), _ptr(dst) if dst is not None else None))
 
+    def draw_batch_async(self, setups: Sequence[FrameSetup], dst: np.ndarray) -> int:
+        """cvx_draw_batch_async: enqueue the batch and return its number at once; batch_wait(number) returns when its frames are in `dst`
+        (pinned host array, one frame per view). A further asynchronous batch (into another destination) renders while this one's frames
+        are still being copied out."""
+        arr = (FrameSetup * len(setups))(*setups)
+        b = C.c_int64(-1)
+        self._ck(lib.cvx_draw_batch_async(self._ctx, arr, len(setups), _ptr(dst), C.byref(b)))
+        return b.value
+
+    def draw_world_batch_async(self, poses, dst: np.ndarray, limit_horizon: bool = True) -> int:
+        """cvx_draw_world_batch_async. `poses` may be what pose_batch() returned (marshalled once, reused every call)."""
+        arr = poses if not isinstance(poses, (list, tuple)) else self.pose_batch(poses)
+        lods = (C.c_float * LOD_LEVELS)(*[float(x) for x in self.lod_distances])
+        b = C.c_int64(-1)
+        self._ck(lib.cvx_draw_world_batch_async(self._ctx, arr, len(arr), C.byref(lods), int(limit_horizon), _ptr(dst), C.byref(b)))
+        return b.value
+
+    def pose_batch(self, poses: Sequence[CameraPose]):
+        """The poses as the C array cvx_draw_world_batch(_async) takes."""
+        return (Pose * len(poses))(*[p.to_native(self.width, self.height) for p in poses])
+
+    def batch_wait(self, batch: int):
+        self._ck(lib.cvx_batch_wait(self._ctx, batch))
+
     def sync(self):
         self._ck(lib.cvx_sync(self._ctx))
 

@@ -121,6 +121,9 @@ SYMBOLS = {
     "cvx_blit_owned": (C.c_int, [_P, C.POINTER(FrameSetup), _I32, _I32, _P]),
     "cvx_draw_batch": (C.c_int, [_P, C.POINTER(FrameSetup), _I32, _P]),
     "cvx_draw_world_batch": (C.c_int, [_P, C.POINTER(Pose), _I32, C.POINTER(_F * LOD_LEVELS), _I32, _P]),
+    "cvx_draw_batch_async": (C.c_int, [_P, C.POINTER(FrameSetup), _I32, _P, C.POINTER(C.c_int64)]),
+    "cvx_draw_world_batch_async": (C.c_int, [_P, C.POINTER(Pose), _I32, C.POINTER(_F * LOD_LEVELS), _I32, _P, C.POINTER(C.c_int64)]),
+    "cvx_batch_wait": (C.c_int, [_P, C.c_int64]),
     "cvx_sync": (C.c_int, [_P]),
     "cvx_read_frame": (C.c_int, [_P, _P, _I64]),
     "cvx_read_raybuffer": (C.c_int, [_P, _I32, _P, _I64]),

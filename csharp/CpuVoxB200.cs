@@ -57,6 +57,8 @@ public static unsafe class CpuVoxB200
 	[DllImport(LIB)] public static extern int cvx_set_resolution(IntPtr ctx, int width, int height);
 	[DllImport(LIB)] public static extern int cvx_draw(IntPtr ctx, ref FrameSetup setup);
 	[DllImport(LIB)] public static extern int cvx_draw_batch(IntPtr ctx, FrameSetup* setups, int nViews, void* dstFrames);
+	[DllImport(LIB)] public static extern int cvx_draw_batch_async(IntPtr ctx, FrameSetup* setups, int nViews, void* dstFrames, out long batch); // returns once enqueued
+	[DllImport(LIB)] public static extern int cvx_batch_wait(IntPtr ctx, long batch);                                                       // that batch's frames are in dstFrames
 	[DllImport(LIB)] public static extern int cvx_sync(IntPtr ctx);
 	[DllImport(LIB)] public static extern int cvx_read_frame(IntPtr ctx, void* dstArgb, long bytes);
 	[DllImport(LIB)] public static extern int cvx_read_raybuffer(IntPtr ctx, int which, void* dstArgb, long bytes);

@@ -128,6 +128,13 @@ int cvx_blit_owned(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t ray_begin
  * With dst_frames the frames pass through a pool of up to 32 device framebuffers (allocated on first use, W*H*4 bytes each) that
  * a copy stream drains in view order, so rendering runs ahead of the device->host copies instead of waiting for them. */
 int cvx_draw_batch(cvx_ctx* ctx, const cvx_frame_setup* setups, int32_t n_views, void* dst_frames);
+/* Asynchronous form (dst_frames required, n_views >= 2): returns as soon as the batch is enqueued and hands out a batch number;
+ * cvx_batch_wait(batch) returns when that batch's frames are in dst_frames (cvx_sync waits for everything). A further asynchronous
+ * batch may be issued before the previous one has finished — into a different destination — and then renders while the previous
+ * batch's frames are still being copied out: the way to stream batches without idling the GPU during the copy backlog at the end of
+ * each one. Up to 4 batches may be outstanding. The views of consecutive batches use the same buffer sets in order. */
+int cvx_draw_batch_async(cvx_ctx* ctx, const cvx_frame_setup* setups, int32_t n_views, void* dst_frames, int64_t* out_batch);
+int cvx_batch_wait(cvx_ctx* ctx, int64_t batch);
 int cvx_sync(cvx_ctx* ctx);
 
 /* ---- outputs --------------------------------------------------------------------------------
@@ -284,6 +291,9 @@ int cvx_host_frame_setup(const cvx_pose* pose, const float lod_distances[CVX_LOD
  * context's resolution (pixel_width / pixel_height of the poses are ignored) and renders the views like cvx_draw_batch. */
 int cvx_draw_world_batch(cvx_ctx* ctx, const cvx_pose* poses, int32_t n_views, const float lod_distances[CVX_LOD_LEVELS],
                          int32_t limit_rotation_horizon, void* dst_frames);
+/* The same through cvx_draw_batch_async: returns once enqueued, cvx_batch_wait(*out_batch) for the frames. */
+int cvx_draw_world_batch_async(cvx_ctx* ctx, const cvx_pose* poses, int32_t n_views, const float lod_distances[CVX_LOD_LEVELS],
+                               int32_t limit_rotation_horizon, void* dst_frames, int64_t* out_batch);
 /* BenchmarkPath.anim sampled at clip time t in [0, 1.15] (UnityManager.cs:86-87): position is
  * the normalised curve value times the world dimensions; rotation from the Euler curves. */
 void cvx_host_benchmark_pose(float clip_time, const int32_t world_dims[3], cvx_pose* inout_pose);

@@ -340,6 +340,50 @@ def test_draw_batch_equals_individual_draws(cv, rm, mill_world):
         rm.set_frames_in_flight(17)
 
 
+def test_asynchronous_batches_deliver_the_same_frames(cv, rm, mill_world):
+    """cvx_draw_batch_async: three batches outstanding at once (each into its own pinned destination, the later ones rendering while the
+    earlier ones' frames are still being copied out; the framebuffer pool and the last view's buffer are shared between them), waited for
+    out of order, mixed with synchronous calls: every frame equals the single draw."""
+    rm.upload_world(mill_world)
+    W, H = 640, 360
+    rm.set_resolution(W, H)
+    setups = [rm.make_setup(pose_for(cv, mill_world, spec)) for spec in POSES]
+    singles = []
+    for s in setups:
+        rm.draw_setup(s)
+        rm.sync()
+        singles.append(rm.read_frame().copy())
+    orders = [[(3 * i + b) % len(setups) for i in range(41)] for b in range(3)]   # longer than the pool of 32 framebuffers
+    dsts = [cv.alloc_pinned((41, H, W)) for _ in range(3)]
+    for k in (6, 2):
+        rm.set_frames_in_flight(k)
+        for d in dsts:
+            d[:] = 0
+        ids = [rm.draw_batch_async([setups[j] for j in orders[b]], dsts[b]) for b in range(3)]
+        assert ids[1] == ids[0] + 1 and ids[2] == ids[0] + 2
+        for b in (1, 0, 2):
+            rm.batch_wait(ids[b])
+            for i, j in enumerate(orders[b]):
+                assert np.array_equal(dsts[b][i], singles[j]), (k, b, i)
+        assert np.array_equal(rm.read_frame(), singles[orders[2][-1]])       # the last view of the last batch stays readable
+        # a synchronous batch right behind an asynchronous one
+        dsts[0][:] = 0; dsts[1][:] = 0
+        b0 = rm.draw_world_batch_async([pose_for(cv, mill_world, POSES[j]) for j in orders[0]], dsts[0])
+        rm.draw_batch([setups[j] for j in orders[1]], dsts[1])
+        for i, j in enumerate(orders[1]):
+            assert np.array_equal(dsts[1][i], singles[j]), (k, "sync", i)
+        rm.batch_wait(b0)
+        for i, j in enumerate(orders[0]):
+            assert np.array_equal(dsts[0][i], singles[j]), (k, "async world", i)
+    with pytest.raises(cv.CvxError):
+        rm.batch_wait(10 ** 6)
+    with pytest.raises(cv.CvxError):
+        rm.draw_batch_async(setups[:1], dsts[0])
+    rm.set_frames_in_flight(6)
+    for d in dsts:
+        cv.native.lib.cvx_free_pinned(d.ctypes.data)
+
+
 def test_draw_world_batch_equals_setup_batch(cv, rm, mill_world):
     """cvx_draw_world_batch (poses in, host setup inside the library) == cvx_draw_batch of the setups the host computes itself."""
     rm.upload_world(mill_world)
