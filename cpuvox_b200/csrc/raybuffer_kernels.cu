@@ -308,38 +308,11 @@ __device__ __forceinline__ void reduce_pixel_horizon(RowState& rw, int& bMin, in
 
 struct Acc { unsigned long long dda_steps, columns_nonempty, runs_visited, px_voxel, px_sky; };
 
-// Load whose result is never used: pulls the line into L1/L2 ahead of the dependent loads of the column body.
-__device__ __forceinline__ void touch(const uint32_t* p) {
-#ifdef CVX_EMU
-    (void)p;
-#else
-    asm volatile("{ .reg .u32 sink; ld.global.nc.u32 sink, [%0]; }" :: "l"(p));
-#endif
-}
-
 /*
  * phase1_kernel<G, COUNTERS>: one GROUP of G lanes (8, 16 or 32) per raybuffer row, 32/G rows per warp.
  * Neighbouring rows (adjacent rays of one segment) share a warp: they walk nearly the same columns, so the groups of
  * a warp stay mostly convergent while the number of rays in flight per SM grows by 32/G.
  */
-#ifndef CVXD_HOT_SKIP /* skip cached columns none of whose lanes can still write (exact, from the hot-lane masks) */
-#define CVXD_HOT_SKIP 1
-#endif
-#ifndef CVXD_HULL /* hull test for columns that are not in the round cache: since the hot-lane masks it costs more than it saves (off) */
-#define CVXD_HULL 0
-#endif
-#ifndef CVXD_FOLLOW_CULL /* leave columns the current frustum culls out of a new round: measured slightly negative (off) */
-#define CVXD_FOLLOW_CULL 0
-#endif
-#ifndef CVXD_TOUCH /* prefetch of each non-empty column's first boundary record at batch time: neutral since the round cache (off) */
-#define CVXD_TOUCH 0
-#endif
-#ifndef CVXD_DEFER_STORE /* store of a side-span pixel deferred to the next gather: neutral, costs two registers (off) */
-#define CVXD_DEFER_STORE 0
-#endif
-#ifndef CVXD_MULTI_COL
-#define CVXD_MULTI_COL 1
-#endif
 #ifndef CVXD_MIN_CTAS_PER_SM /* with 32-thread CTAs: 21 -> ptxas settles on 80 registers (25 resident warps per SM); measured best */
 #define CVXD_MIN_CTAS_PER_SM 21
 #endif
@@ -431,8 +404,6 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
         const int maskX = world.dim_x - 1, maskZ = world.dim_z - 1;
         // unlerp(0, worldMaxY, y) = (y - 0) / (worldMaxY - 0): for a power-of-two height the quotient is exactly y * 2^-k
 
-        // CVXD_DEFER_STORE builds only (off: measured neutral): a side-span pixel's store waits until this lane's next gather
-        int pendY = -1; uint32_t pendColor = 0u;
         bool terminated = false; // ray ended inside the loop: skybox the rest and stop
         bool reachedEnd = false; // far clip or world exit
         while (!terminated && !reachedEnd) {
@@ -498,11 +469,6 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
             uint4 hdr = make_uint4(0, 0, 0, 0);
             if (gl < n) hdr = __ldg(world.lods[myLod].headers + myIdx);
             const bool myNonEmpty = (hdr.y & 0xffffu) != 0u;
-            // start fetching the run list of every non-empty column of the batch now; the column bodies below find it cached
-            if (CVXD_TOUCH && myNonEmpty) {
-                if (FAST) touch((const uint32_t*)(world.lods[myLod].bounds + hdr.w + (ITER > 0 ? 0u : (hdr.y & 0xffffu))));
-                else touch(world.lods[myLod].elements + hdr.x + (ITER > 0 ? 1u : (hdr.y & 0xffffu)));
-            }
             const float myWorldMin = (float)(hdr.y >> 16), myWorldMax = (float)(hdr.z & 0xffffu);
             uint32_t remaining = GBALLOT(myNonEmpty);
             int cellsDone = n + (endKind == 1 ? 1 : 0); // the out-of-world probe counts as a step
@@ -528,28 +494,6 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
             bool r_solid = false;         // this lane holds a valid, non-air run
             const int myRunCount = (int)(hdr.y & 0xffffu);
 
-            // Product builds (no counters): screen-axis hull of this lane's column — the projections of its solid extent
-            // [worldMin, worldMax] on the last and next line. Every side span lies between two points of the last line and every cap
-            // span between a last-line and a next-line point of one height (:478-481,554-562), and with all four corners in front of
-            // the near plane the projection is monotone along those lines, so all spans of the column lie inside the hull (+-1 pixel
-            // for rounding). While the frustum is valid (not the float.Epsilon sentinel) a column is entered without side effects unless
-            // one of its spans holds an unwritten pixel (see span_would_write), so a column whose hull holds none is skipped exactly
-            // like a culled one. Counter builds enter every column the reference enters, to count its runs.
-            int hullMin = INT_MIN / 2, hullMax = INT_MAX / 2; // "cannot tell": never skipped
-            if (CVXD_HULL && !COUNTERS && myNonEmpty) {
-                const float pLo = unlerpf(0.0f, worldMaxY, myWorldMin), pHi = unlerpf(0.0f, worldMaxY, myWorldMax);
-                const F3 bL = F3{planeBottom.x + planeDir.x * myDl, planeBottom.y + planeDir.y * myDl, planeBottom.z + planeDir.z * myDl};
-                const F3 tL = F3{planeTop.x + planeDir.x * myDl, planeTop.y + planeDir.y * myDl, planeTop.z + planeDir.z * myDl};
-                const F3 bN = F3{planeBottom.x + planeDir.x * myDn, planeBottom.y + planeDir.y * myDn, planeBottom.z + planeDir.z * myDn};
-                const F3 tN = F3{planeTop.x + planeDir.x * myDn, planeTop.y + planeDir.y * myDn, planeTop.z + planeDir.z * myDn};
-                const F3 q0 = lerp3(bL, tL, pLo), q1 = lerp3(bL, tL, pHi), q2 = lerp3(bN, tN, pLo), q3 = lerp3(bN, tN, pHi);
-                if (q0.y > 0.0f && q1.y > 0.0f && q2.y > 0.0f && q3.y > 0.0f) { // all in front of the near plane (z' > 0 <=> w > near)
-                    const float a0 = q0.x / q0.z, a1 = q1.x / q1.z, a2 = q2.x / q2.z, a3 = q3.x / q3.z;
-                    const float lo = fminf(fminf(a0, a1), fminf(a2, a3)), hi = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
-                    if (lo > -1.0e6f && hi < 1.0e6f) { hullMin = (int)floorf(lo) - 1; hullMax = (int)ceilf(hi) + 1; } // NaN fails both tests
-                }
-            }
-
             while (remaining) {
                 STAMP(2);
                 EMU_STAT(1); // select iterations
@@ -563,12 +507,11 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                     const float newMin = camY + frustumDirMinWorld * distBot;
                     const bool outOfWorld = newMin > worldMaxY || newMax < 0.0f;      // frustum left the world: ray ends
                     const bool culled = myWorldMin > newMax || myWorldMax < newMin;   // column outside the writable world bounds
-                    // cannot write, hence no side effects: exactly known for a column in the round cache, by its hull otherwise
+                    // cannot write, hence no side effects: exactly known for a column in the round cache (product builds; counter builds
+                    // enter every column the reference enters, to count its runs)
                     bool inert = false;
-                    if ((CVXD_HULL || CVXD_HOT_SKIP) && !COUNTERS && !culled && myNonEmpty) {
-                        if (CVXD_HOT_SKIP && ((roundCols >> gl) & 1u)) inert = !((roundHotS | roundHotC) & ((myRunCount >= 32 ? FULL_MASK : ((1u << myRunCount) - 1u)) << myBase));
-                        else if (CVXD_HULL) inert = !span_would_write(rw, hullMin, hullMax);
-                    }
+                    if (!COUNTERS && !culled && myNonEmpty && ((roundCols >> gl) & 1u))
+                        inert = !((roundHotS | roundHotC) & ((myRunCount >= 32 ? FULL_MASK : ((1u << myRunCount) - 1u)) << myBase));
                     const uint32_t cand = GBALLOT(myNonEmpty && (outOfWorld || !(culled || inert))) & remaining;
                     if (!cand) {
                         if (COUNTERS && gl == 0) acc.columns_nonempty += __popc(remaining);
@@ -671,14 +614,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                         // to be entered, as long as their runs fit in the G lanes. One run per lane: fetch, world-Y bounds (segmented
                         // prefix sum), and the projected side/cap spans — the float-heavy part — once for all of them.
                         EMU_STAT(4); // rounds formed
-                        uint32_t follow = (CVXD_MULTI_COL && !tall) ? remaining : 0u;
-                        if (CVXD_FOLLOW_CULL && follow && frustumDirMaxWorld != EPS) {
-                            const float distTop = frustumDirMaxWorld > 0.0f ? myDn : myDl;
-                            const float distBot = frustumDirMinWorld < 0.0f ? myDn : myDl;
-                            const float newMax = camY + frustumDirMaxWorld * distTop;
-                            const float newMin = camY + frustumDirMinWorld * distBot;
-                            follow &= GBALLOT(myNonEmpty && !(myWorldMin > newMax || myWorldMax < newMin));
-                        }
+                        const uint32_t follow = !tall ? remaining : 0u;
                         const uint32_t consider = (1u << c) | follow;
                         // lanes a column needs: one per run, or (FAST) one per boundary = runs + 1; a pass of a tall column takes G
                         // boundaries, the last of which opens the next pass
@@ -953,10 +889,7 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
                                         float u = wy / wx;
                                         idx = max(0, min(jLen - 1, f2i(floorf(u)))) + jCi;
                                     }
-                                    if (CVXD_DEFER_STORE) {
-                                        if (pendY >= 0) row[pendY] = pendColor; // the gather issued by the previous commit has long arrived
-                                        pendColor = __ldg(colColors + idx); pendY = y;
-                                    } else row[y] = __ldg(colColors + idx);
+                                    row[y] = __ldg(colColors + idx);
                                 }
                             }
                         }
@@ -977,7 +910,6 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
             if (COUNTERS && gl == 0) acc.dda_steps += cellsDone;
             if (endKind != 0) reachedEnd = true;
         }
-        if (pendY >= 0) row[pendY] = pendColor;
         STAMP(7);
         // WriteSkybox :699-708 — :248,268,323,401,419,537,606,619 all end here
         __syncwarp(gmask);

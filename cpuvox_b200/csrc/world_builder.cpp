@@ -553,12 +553,18 @@ int cvx_world_file_read(const char* path, int32_t out_dims[3], int32_t* out_worl
     int64_t table[2 * CVX_LOD_LEVELS];
     if (fread(table, 16, (size_t)hdr[3], f) != (size_t)hdr[3]) { fclose(f); return CVX_ERR_FORMAT; }
     for (int i = 0; i < CVX_LOD_LEVELS; i++) { out_blobs[i] = nullptr; out_blob_bytes[i] = 0; }
+    // an error in the middle of the file hands nothing out: the blobs read so far are freed again
+    auto bail = [&](int code) {
+        for (int i = 0; i < CVX_LOD_LEVELS; i++) { free(out_blobs[i]); out_blobs[i] = nullptr; out_blob_bytes[i] = 0; }
+        fclose(f);
+        return code;
+    };
     for (int i = 0; i < hdr[3]; i++) {
         int64_t off = table[2 * i], len = table[2 * i + 1];
-        if (off < 0 || len < 0 || fseek(f, (long)off, SEEK_SET) != 0) { fclose(f); return CVX_ERR_FORMAT; }
+        if (off < 0 || len < 0 || fseek(f, (long)off, SEEK_SET) != 0) return bail(CVX_ERR_FORMAT);
         void* p = malloc((size_t)std::max<int64_t>(1, len));
-        if (!p) { fclose(f); return CVX_ERR_OUT_OF_MEMORY; }
-        if (fread(p, 1, (size_t)len, f) != (size_t)len) { free(p); fclose(f); return CVX_ERR_FORMAT; }
+        if (!p) return bail(CVX_ERR_OUT_OF_MEMORY);
+        if (fread(p, 1, (size_t)len, f) != (size_t)len) { free(p); return bail(CVX_ERR_FORMAT); }
         out_blobs[i] = p; out_blob_bytes[i] = len;
     }
     fclose(f);
