@@ -8,7 +8,8 @@ import cpuvox_b200 as cv
 world = cv.World.synthetic(0, (2048, 2048, 2048), seed=1234)
 rm = cv.RenderManager(0)
 rm.upload_world(world)
-rm.set_resolution(1920, 1080)
+W, H = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else '1920x1080').split('x')]
+rm.set_resolution(W, H)
 pose = cv.CameraPose.from_euler((1024.0, 1700.0, 1024.0), (60.0, 30.0, 0.0), far_clip=4096.0)
 s = rm.make_setup(pose)
 for g in (32, 16, 8):
