@@ -69,7 +69,7 @@ struct cvx_ctx {
     bool poolUsed[CVX_POOL_FRAMES] = {false};
     // asynchronous batches (cvx_draw_batch_async): batchDone[b % 4] is recorded on the copy stream behind batch b's last copy
     cudaEvent_t batchDone[4] = {nullptr, nullptr, nullptr, nullptr};
-    int64_t batchSeq = 0;
+    int64_t batchSeq = 0, batchSettled = 0;   // batches issued / batches the context's stream has been ordered behind
     uint32_t* externalFrame = nullptr;
     uint32_t* presentStage = nullptr;   // cvx_present with a host destination / cvx_present_jpeg: converted frame (W*H*4 bytes)
     cvxjpeg::Encoder* jpeg = nullptr;   // created by the first cvx_present_jpeg
@@ -168,6 +168,15 @@ uint32_t* slot_lr(cvx_ctx* ctx, int s) { return s == 0 ? ctx->lr : ctx->extra[s 
 uint32_t* slot_frame(cvx_ctx* ctx, int s) { return s == 0 ? ctx->frames[0] : ctx->extra[s - 1].frame; }
 
 uint32_t* current_target(cvx_ctx* ctx) { return ctx->externalFrame ? ctx->externalFrame : slot_frame(ctx, ctx->lastSlot); }
+
+// An asynchronous batch leaves its device->host copies unjoined (that is its point); its last view's frame lives in a slot's own
+// framebuffer until copied. Whatever else is about to WRITE a slot framebuffer first orders the context's stream behind those copies.
+cudaError_t settle_async(cvx_ctx* ctx) {
+    if (ctx->batchSettled == ctx->batchSeq) return cudaSuccess;
+    ctx->batchSettled = ctx->batchSeq;
+    return cudaStreamWaitEvent(ctx->stream, ctx->batchDone[(ctx->batchSeq - 1) % 4], 0);
+}
+
 
 // ---- frame ring: device-side flow control between ranks (no host barrier, no collective on the data path) ------------------
 #define CVX_RING_MAX_RANKS 64
@@ -485,6 +494,7 @@ int cvx_blit_rows(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t row_begin,
     if (row_begin < 0) row_begin = 0;
     b.row_begin = row_begin; b.row_end = row_end;
     CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, settle_async(ctx));
     CU(ctx, cvxd_launch_phase2(b, ctx->stream));
     if (row_end > row_begin) ctx->launches++;
     return CVX_OK;
@@ -501,6 +511,7 @@ int cvx_blit_owned(cvx_ctx* ctx, const cvx_frame_setup* setup, int32_t ray_begin
     if (ray_begin < 0) ray_begin = 0;
     b.ray_begin = ray_begin; b.ray_end = ray_end; b.owned_only = 1;
     CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, settle_async(ctx));
     CU(ctx, cvxd_launch_phase2(b, ctx->stream));
     ctx->launches++;
     return CVX_OK;
@@ -545,6 +556,7 @@ int cvx_draw(cvx_ctx* ctx, const cvx_frame_setup* setup) {
     int r = check_ready(ctx, setup);
     if (r) return r;
     CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, settle_async(ctx));
     ctx->lastSlot = 0;
     return draw_into(ctx, setup, 0, current_target(ctx), true);
 }
@@ -572,6 +584,7 @@ static int draw_batch_impl(cvx_ctx* ctx, const cvx_frame_setup* setups, int32_t 
     const bool pooled = dst_frames && !ctx->externalFrame && n_views > 1;
     const int M = CVX_POOL_FRAMES < n_views - 1 ? CVX_POOL_FRAMES : n_views - 1;
     if (pooled && (r = ensure_pool(ctx, M))) return r;
+    if (!pooled) CU(ctx, settle_async(ctx));   // this batch writes the slots' own framebuffers
     CU(ctx, cudaEventRecord(ctx->evBatchStart, ctx->stream)); // the slots start after everything queued on the context's stream
     for (int s = 1; s < K; s++) CU(ctx, cudaStreamWaitEvent(slot_stream(ctx, s), ctx->evBatchStart, 0));
     cudaError_t ce = cudaSuccess;
@@ -696,6 +709,7 @@ int cvx_blit_raybuffer(cvx_ctx* ctx, int32_t which) {
     if (ctx->width <= 0) return fail(ctx, CVX_ERR_NO_RESOLUTION, "no resolution set");
     const int W = ctx->width, H = ctx->height;
     CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, settle_async(ctx));
     const uint32_t* buf = which == 0 ? slot_td(ctx, ctx->lastSlot) : slot_lr(ctx, ctx->lastSlot);
     CU(ctx, cvxd_launch_raybuffer_view(buf, which == 0 ? W + 2 * H : 2 * W + H, which == 0 ? H : W, current_target(ctx), W, H, ctx->stream));
     ctx->launches++;

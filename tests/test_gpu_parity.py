@@ -375,6 +375,16 @@ def test_asynchronous_batches_deliver_the_same_frames(cv, rm, mill_world):
         rm.batch_wait(b0)
         for i, j in enumerate(orders[0]):
             assert np.array_equal(dsts[0][i], singles[j]), (k, "async world", i)
+        # a single draw right behind an asynchronous batch (with 2 views in flight the batch's last view sits in the framebuffer the single
+        # draw writes): the draw is ordered behind the batch's copies
+        dsts[2][:] = 0
+        b2 = rm.draw_batch_async([setups[j] for j in orders[2]], dsts[2])
+        rm.draw_setup(setups[5])
+        rm.blit_raybuffer(0)
+        rm.batch_wait(b2)
+        for i, j in enumerate(orders[2]):
+            assert np.array_equal(dsts[2][i], singles[j]), (k, "single behind async", i)
+        rm.sync()
     with pytest.raises(cv.CvxError):
         rm.batch_wait(10 ** 6)
     with pytest.raises(cv.CvxError):
