@@ -374,9 +374,555 @@ phase1_kernel(const __grid_constant__ cvxd_world world, const __grid_constant__ 
         for (int y = rw.orig_min + gl; y <= rw.orig_max; y += G) row[y] = SKYBOX_ARGB;
         if (COUNTERS && gl == 0 && rw.orig_max >= rw.orig_min) acc.px_sky += rw.orig_max - rw.orig_min + 1;
     } else {
-#define P1_PIPELINED 0
-#include "phase1_body.inc"
-#undef P1_PIPELINED
+        for (int w = gl; w < seenWords; w += G) rw.seen[w] = 0u; // stackalloc, zero-initialised (:208)
+        __syncwarp(gmask);
+
+        Dda ray = rs.dda;
+        int lod = rs.lod;
+        int voxelScale = 1 << lod;
+        const float farClip = f.far_clip;
+        float lodMax = f.lod_dist[lod];
+        #define worldMaxY (world.dim_y_f) /* a constant-bank operand, not a register */
+        const float camY = f.pos_y;
+        #define cameraPosYNormalized (f.cam_y_norm)
+        constexpr int ITER = INV ? -1 : 1; // RenderJob.Execute :174-178 (INV = InverseElementIterationDirection, one kernel instance per direction)
+        const float EPS = float_epsilon();
+        float frustumDirMaxWorld = EPS, frustumDirMinWorld = EPS;
+
+        // SetupProjectedPlaneParams :622-651
+        F3 planeBottom, planeTop, planeDir;
+        {
+            float top[4], bot[4], dir[4];
+            project(f.wts, ray.start_x, worldMaxY, ray.start_z, 1.0f, top);
+            project(f.wts, ray.start_x, 0.0f, ray.start_z, 1.0f, bot);
+            project(f.wts, ray.dir_x, 0.0f, ray.dir_z, 0.0f, dir);
+            const int a = sg.axis_mapped_to_y ? 1 : 0;
+            planeBottom = F3{bot[a], bot[2], bot[3]};
+            planeTop = F3{top[a], top[2], top[3]};
+            planeDir = F3{dir[a], dir[2], dir[3]};
+        }
+        const int maskX = world.dim_x - 1, maskZ = world.dim_z - 1;
+        // unlerp(0, worldMaxY, y) = (y - 0) / (worldMaxY - 0): for a power-of-two height the quotient is exactly y * 2^-k
+
+        bool terminated = false; // ray ended inside the loop: skybox the rest and stop
+        bool reachedEnd = false; // far clip or world exit
+        while (!terminated && !reachedEnd) {
+            STAMP(1);
+            EMU_STAT(0); // batches
+            // ---- look ahead: the next G cells of the DDA at once, lane k of the group gets cell k -------------------------
+            // Step() (SegmentDDAData.cs:135-150) crosses the x boundary when tMax.x < tMax.y, else the z boundary, and then adds
+            // tDelta to that tMax: the crossing times are the merge of the two sequences X[a] = tMax.x + a additions of tDelta.x and
+            // Z[b] likewise (ties go to z). The two chains are accumulated serially (same float additions as the reference), lane j
+            // keeps X[j] and Z[j]; lane k then finds by a merge-path binary search how many of its first k steps were x steps —
+            // a_k = the largest a with X[a-1] < Z[k-a] — which gives its cell, its last/next distances and its header address.
+            if (ray.dl >= lodMax) { // :237-243, tested once per visited cell: here for cell 0, for later cells by cutting the batch
+                dda_next_lod(ray, voxelScale);
+                lod++; voxelScale *= 2;
+                lodMax = f.lod_dist[lod];
+            }
+            float myX = ray.tmx, myZ = ray.tmz, xEnd, zEnd;
+            {
+                float x = ray.tmx, z = ray.tmz;
+#pragma unroll
+                for (int j = 1; j < G; j++) {
+                    x += ray.tdx; z += ray.tdz;
+                    if (gl == j) { myX = x; myZ = z; }
+                }
+                xEnd = x + ray.tdx; zEnd = z + ray.tdz; // X[G], Z[G]
+            }
+            int aK = 0;
+            {
+                int lo = 0, hi = gl;
+#pragma unroll
+                for (int it = 0; it < (G == 32 ? 5 : (G == 16 ? 4 : 3)); it++) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    const float xv = GSHFL(myX, mid > 0 ? mid - 1 : 0), zv = GSHFL(myZ, gl - mid >= 0 ? gl - mid : 0);
+                    if (lo < hi) { if (xv < zv) lo = mid; else hi = mid - 1; }
+                }
+                aK = lo;
+            }
+            const int bK = gl - aK;
+            const float xa = GSHFL(myX, aK), zb = GSHFL(myZ, bK); // tMax of my cell
+            const bool xStep = xa < zb;                          // which boundary Step() crosses leaving my cell
+            const float myDn = xStep ? xa : zb;                  // crossed distance = next intersection of my cell
+            float myDl = __shfl_up_sync(gmask, myDn, 1, G);      // the previous cell's crossing is my last intersection
+            if (gl == 0) myDl = ray.dl;
+            const int cellX = ray.px + aK * ray.sx, cellZ = ray.pz + bK * ray.sz;
+            const bool oob = ((cellX & maskX) != cellX) || ((cellZ & maskZ) != cellZ);   // World.cs:135-138
+            // first event in walk order: LOD switch before cell k (k >= 1), world exit at cell k, far clip after cell k (:613-615)
+            const uint32_t swMask = GBALLOT(gl >= 1 && myDl >= lodMax), oobMask = GBALLOT(oob), farMask = GBALLOT(myDn >= farClip);
+            const int kS = swMask ? __ffs(swMask) - 1 : G, kO = oobMask ? __ffs(oobMask) - 1 : G, kF = farMask ? __ffs(farMask) - 1 : G;
+            int n, endKind = 0; // 1 = next cell is outside the world, 2 = far clip crossed after the last cell
+            if (kS <= kO && kS <= kF) n = kS;                    // cut: the next batch starts with the LOD switch (or n == G: plain end of batch)
+            else if (kO <= kF) { n = kO; endKind = 1; }
+            else { n = kF + 1; endKind = 2; }
+            const int myIdx = (cellX >> lod) * world.lods[lod].mul_x + (cellZ >> lod); // GetIndexKnownInBounds World.cs:145-149
+            const int myLod = lod;                               // one LOD per batch
+            if (endKind == 0 && n > 0) {                         // advance the ray to the cell after the batch
+                const int aN = GSHFL(aK + (xStep ? 1 : 0), n - 1), bN = n - aN;
+                const float tx = GSHFL(myX, aN < G ? aN : 0), tz = GSHFL(myZ, bN < G ? bN : 0);
+                ray.tmx = aN < G ? tx : xEnd; ray.tmz = bN < G ? tz : zEnd;
+                ray.px += aN * ray.sx; ray.pz += bN * ray.sz;
+                ray.dl = GSHFL(myDn, n - 1);
+                ray.dn = minf_(ray.tmx, ray.tmz);
+            }
+            uint4 hdr = make_uint4(0, 0, 0, 0);
+            if (gl < n) hdr = __ldg(world.lods[myLod].headers + myIdx);
+            const bool myNonEmpty = (hdr.y & 0xffffu) != 0u;
+            const float myWorldMin = (float)(hdr.y >> 16), myWorldMax = (float)(hdr.z & 0xffffu);
+            uint32_t remaining = GBALLOT(myNonEmpty);
+            int cellsDone = n + (endKind == 1 ? 1 : 0); // the out-of-world probe counts as a step
+
+            // Round cache: span geometry of several consecutive columns of this batch, one run per lane (see form_round below).
+            uint32_t roundCols = 0u;      // batch cells whose runs are cached in the lanes
+            uint32_t roundInvalid = 0u;   // lanes holding an invalid element (Length == 0), which ends its column (:445-447)
+            int myBase = 0;               // batch lane c: first round lane of column c
+            // per-lane cached run: element fields, world-Y bounds, side span and cap span (none of it depends on the written-pixel state)
+            // (what only the commit of a span needs — colour indices, unrounded bounds, 1/w and u/w of both ends — is parked in
+            // shared memory, cache[field * G + lane], and read back by the whole group at the committing lane's index)
+            int r_ci = 0, r_sMin = 0, r_sMax = 0, r_cMin = 0, r_cMax = 0, r_capKind = 0;
+            bool r_sideClip = false, r_capClip = false;
+            float r_eMin = 0.0f, r_eMax = 0.0f;
+            // FAST rounds: one BOUNDARY per lane (see world_transcode.h); the lane also owns the run between its boundary and the
+            // next lane's. Kept for the commit: the run's length, its cap colour and the boundary's point on the last line.
+            int r_len = 0; uint32_t r_capColor = 0u; float bFx = 0.0f, bFy = 0.0f, bFz = 0.0f;
+            // Lanes of the round whose side / cap span held an unwritten pixel of the writable range when the round was formed. Written
+            // pixels only grow and the writable range only shrinks, so these stay SUPERSETS of the spans that can still write: a
+            // cached column none of whose lanes is set is inert (skipped like a culled one, see the hull comment below), and the
+            // commit loop looks at the set lanes only.
+            uint32_t roundHotS = 0u, roundHotC = 0u;
+            bool r_solid = false;         // this lane holds a valid, non-air run
+            const int myRunCount = (int)(hdr.y & 0xffffu);
+
+            while (remaining) {
+                STAMP(2);
+                EMU_STAT(1); // select iterations
+                // ---- next column that is not culled by the narrowed frustum (:261-281), found for all columns at once ----
+                int c;
+                float worldBoundsMin = 0.0f, worldBoundsMax = worldMaxY;
+                if (frustumDirMaxWorld != EPS) {
+                    const float distTop = frustumDirMaxWorld > 0.0f ? myDn : myDl;
+                    const float distBot = frustumDirMinWorld < 0.0f ? myDn : myDl;
+                    const float newMax = camY + frustumDirMaxWorld * distTop;
+                    const float newMin = camY + frustumDirMinWorld * distBot;
+                    const bool outOfWorld = newMin > worldMaxY || newMax < 0.0f;      // frustum left the world: ray ends
+                    const bool culled = myWorldMin > newMax || myWorldMax < newMin;   // column outside the writable world bounds
+                    // cannot write, hence no side effects: exactly known for a column in the round cache (product builds; counter builds
+                    // enter every column the reference enters, to count its runs)
+                    bool inert = false;
+                    if (!COUNTERS && !culled && myNonEmpty && ((roundCols >> gl) & 1u))
+                        inert = !((roundHotS | roundHotC) & ((myRunCount >= 32 ? FULL_MASK : ((1u << myRunCount) - 1u)) << myBase));
+                    const uint32_t cand = GBALLOT(myNonEmpty && (outOfWorld || !(culled || inert))) & remaining;
+                    if (!cand) {
+                        if (COUNTERS && gl == 0) acc.columns_nonempty += __popc(remaining);
+                        remaining = 0u;
+                        break;
+                    }
+                    c = __ffs(cand) - 1;
+                    const uint32_t upto = remaining & ((2u << c) - 1u);
+                    if (COUNTERS && gl == 0) acc.columns_nonempty += __popc(upto);
+                    remaining &= ~upto;
+                    if (GSHFL((int)outOfWorld, c)) { terminated = true; cellsDone = c + 1; break; }
+                    worldBoundsMin = GSHFL(newMin, c); worldBoundsMax = GSHFL(newMax, c);
+                } else {
+                    c = __ffs(remaining) - 1;
+                    remaining &= remaining - 1;
+                    if (COUNTERS && gl == 0) acc.columns_nonempty++;
+                }
+                const float distLast = GSHFL(myDl, c);
+                const float distNext = GSHFL(myDn, c);
+                const int cLod = GSHFL(myLod, c);
+                const uint32_t hOff = GSHFL(hdr.x, c);
+                const int runCount = GSHFL(myRunCount, c);
+                const int cScale = 1 << cLod;
+
+                if (distLast > 2.0f && frustumDirMaxWorld == EPS) { // re-narrow the frustum :295-422
+                    STAMP(3);
+                    EMU_STAT(2); // renarrows
+                    // The four clip parameters (last/next line x min/max end) and their projections are independent:
+                    // lane L&3 of the group computes one of them (same operations as CameraData.cs:50-121), then they are shared.
+                    const int L = gl & 3;
+                    const float dLine = (L & 2) ? distNext : distLast; // :289-293 for this lane's line
+                    const F3 pMin = F3{planeBottom.x + planeDir.x * dLine, planeBottom.y + planeDir.y * dLine, planeBottom.z + planeDir.z * dLine};
+                    const F3 pMax = F3{planeTop.x + planeDir.x * dLine, planeTop.y + planeDir.y * dLine, planeTop.z + planeDir.z * dLine};
+                    const bool A = pMin.x > pMin.z * rw.fb_max, B = pMax.x > pMax.z * rw.fb_max;
+                    const bool C = pMin.x < pMin.z * rw.fb_min, D = pMax.x < pMax.z * rw.fb_min;
+                    const bool clipped = (A && B) || (!A && !B && C && D);
+                    // ClipMin / ClipMax (CameraData.cs:101-115) against whichever frustum bound this lane's end crosses, if any
+                    const bool isMax = L & 1;
+                    const bool crossHi = isMax ? B : A, crossLo = isMax ? D : C;
+                    float myLerp = isMax ? 1.0f : 0.0f;
+                    if (crossHi || crossLo) {
+                        const float fi = 1.0f / (crossHi ? rw.fb_max : rw.fb_min);
+                        const float c0 = cross2(1.0f, fi, pMax.x, pMax.z), c1 = cross2(1.0f, fi, pMin.x, pMin.z);
+                        const float num = isMax ? c1 : c0, den = isMax ? c1 - c0 : c0 - c1; // one division: c1/(c1-c0) or c0/(c0-c1)
+                        const float q = num / den;
+                        myLerp = isMax ? q : 1.0f - q;
+                    }
+                    const F3 pc = lerp3(pMin, pMax, myLerp);
+                    const float myProj = pc.x / pc.z;
+                    const float lastMinL = GSHFL(myLerp, 0), lastMaxL = GSHFL(myLerp, 1), nextMinL = GSHFL(myLerp, 2), nextMaxL = GSHFL(myLerp, 3);
+                    float mnL = GSHFL(myProj, 0), mxL = GSHFL(myProj, 1), mnN = GSHFL(myProj, 2), mxN = GSHFL(myProj, 3);
+                    const bool clippedLast = GSHFL((int)clipped, 0) != 0, clippedNext = GSHFL((int)clipped, 2) != 0;
+                    float clippedMin, clippedMax, distForMin, distForMax; // which line's distance each frustum direction is taken at
+                    if (clippedLast) {
+                        if (clippedNext) { terminated = true; cellsDone = c + 1; break; }
+                        worldBoundsMin = lerpf(0.0f, worldMaxY, nextMinL); distForMin = distNext;
+                        worldBoundsMax = lerpf(0.0f, worldMaxY, nextMaxL); distForMax = distNext;
+                        clippedMin = mnN; clippedMax = mxN;
+                        if (clippedMax < clippedMin) { float t = clippedMin; clippedMin = clippedMax; clippedMax = t; }
+                    } else if (clippedNext) {
+                        worldBoundsMin = lerpf(0.0f, worldMaxY, lastMinL); distForMin = distLast;
+                        worldBoundsMax = lerpf(0.0f, worldMaxY, lastMaxL); distForMax = distLast;
+                        clippedMin = mnL; clippedMax = mxL;
+                        if (clippedMax < clippedMin) { float t = clippedMin; clippedMin = clippedMax; clippedMax = t; }
+                    } else {
+                        const bool minFromLast = lastMinL < nextMinL, maxFromLast = lastMaxL > nextMaxL;
+                        worldBoundsMin = lerpf(0.0f, worldMaxY, minFromLast ? lastMinL : nextMinL); distForMin = minFromLast ? distLast : distNext;
+                        worldBoundsMax = lerpf(0.0f, worldMaxY, maxFromLast ? lastMaxL : nextMaxL); distForMax = maxFromLast ? distLast : distNext;
+                        if (mxN < mnN) { float t = mxN; mxN = mnN; mnN = t; }
+                        if (mxL < mnL) { float t = mxL; mxL = mnL; mnL = t; }
+                        clippedMin = minf_(mnL, mnN);
+                        clippedMax = maxf_(mxL, mxN);
+                    }
+                    frustumDirMaxWorld = (worldBoundsMax - camY) / distForMax; // :329-330,348-349,359-370
+                    frustumDirMinWorld = (worldBoundsMin - camY) / distForMin;
+                    worldBoundsMin = floorf(worldBoundsMin);
+                    worldBoundsMax = ceilf(worldBoundsMax);
+                    const int writableMin = f2i(floorf(clippedMin));
+                    const int writableMax = f2i(ceilf(clippedMax));
+                    if (writableMax < rw.nf_min || writableMin > rw.nf_max) { terminated = true; cellsDone = c + 1; break; }
+                    if (writableMin > rw.nf_min) rw.nf_min = scan_up(rw.seen, writableMin, rw.orig_max);
+                    if (writableMax < rw.nf_max) rw.nf_max = scan_down(rw.seen, writableMax, rw.orig_min);
+                    if (rw.nf_min > rw.nf_max) { terminated = true; cellsDone = c + 1; break; }
+                }
+
+                const uint32_t* colColors = world.lods[cLod].elements + hOff + runCount + 2; // ColorPointer World.cs:185-188
+
+                // ---- runs of this column (:424-611). A column of at most G runs is resolved from the round cache in one pass; a
+                // taller one goes through the same code G runs at a time (k0 = first run of the pass, yDone = world-Y extent of the
+                // runs before it, in LOD voxels times the LOD scale).
+                const bool tall = FAST ? runCount >= G : runCount > G; // FAST: runCount + 1 boundaries must fit the G lanes
+                int k0 = 0, yDone = 0;
+                bool colStop = false;
+                do {
+                    STAMP(4);
+                    EMU_STAT(3); // column passes
+                    const int runsHere = tall ? (FAST ? (runCount - k0 < G - 1 ? runCount - k0 : G - 1) : (runCount - k0 < G ? runCount - k0 : G)) : runCount;
+                    if (tall || !((roundCols >> c) & 1u)) {
+                        // ---- form a round: this column (pass) plus, if it is not a tall one, the following columns that are likely
+                        // to be entered, as long as their runs fit in the G lanes. One run per lane: fetch, world-Y bounds (segmented
+                        // prefix sum), and the projected side/cap spans — the float-heavy part — once for all of them.
+                        EMU_STAT(4); // rounds formed
+                        const uint32_t follow = !tall ? remaining : 0u;
+                        const uint32_t consider = (1u << c) | follow;
+                        // lanes a column needs: one per run, or (FAST) one per boundary = runs + 1; a pass of a tall column takes G
+                        // boundaries, the last of which opens the next pass
+                        const int v = gl == c ? runsHere + (FAST ? 1 : 0) : (((consider >> gl) & 1u) ? myRunCount + (FAST ? 1 : 0) : 0);
+                        int incl = v;
+#pragma unroll
+                        for (int o = 1; o < G; o <<= 1) { int t = __shfl_up_sync(gmask, incl, o, G); if (gl >= o) incl += t; }
+                        const bool inRound = ((consider >> gl) & 1u) && incl <= G;
+                        roundCols = GBALLOT(inRound);
+                        myBase = incl - v;
+                        if (inRound) scratch[myBase] = gl;           // first lane of each cached column -> its batch cell
+                        const uint32_t startMask = __reduce_or_sync(gmask, inRound ? (1u << myBase) : 0u);
+                        const int totalRuns = GSHFL(incl, 31 - __clz(roundCols));
+                        EMU_STAT_ADD(9, totalRuns);            // lanes used by the rounds
+                        EMU_STAT_ADD(10, __popc(roundCols));   // columns cached by the rounds
+                        EMU_STAT_ADD(11, __popc(consider));    // columns that were candidates for the round
+                        __syncwarp(gmask);
+                        const int myStart = 31 - __clz(startMask & ((2u << gl) - 1u)); // lane 0 always starts a column
+                        const bool hasRun = gl < totalRuns;
+                        const int myCol = hasRun ? scratch[myStart] : c;
+                        const int k = gl - myStart + (myCol == c ? k0 : 0);           // run index inside its column
+                        __syncwarp(gmask);
+                        const float cDl = GSHFL(myDl, myCol), cDn = GSHFL(myDn, myCol);
+                        const uint32_t colOff = GSHFL(hdr.x, myCol);
+                        const int colRuns = GSHFL(myRunCount, myCol);
+                        const uint32_t* colElems = world.lods[cLod].elements + colOff; // one LOD per batch
+                        if (FAST) {
+                            // ---- one boundary per lane: record k of the column (from the top, or from the bottom when iterating
+                            // upwards) = {world-Y of the boundary, RLEElement below it}. The run of lane i lies between the boundaries
+                            // of lanes i and i + 1 (:449-455 without the running sums), and each boundary is projected ONCE on the
+                            // last line (an end of two side spans, :478-502) and once on the next line (an end of one cap span, :554-578).
+                            const uint32_t colB = GSHFL(hdr.w, myCol);
+                            uint2 rec = make_uint2(0u, 0u);
+                            if (hasRun) rec = __ldg(world.lods[cLod].bounds + colB + (ITER > 0 ? k : colRuns - k));
+                            const int yB = (int)rec.x;
+                            const int nextY = __shfl_down_sync(gmask, yB, 1, G);
+                            const uint32_t nextEl = __shfl_down_sync(gmask, rec.y, 1, G);
+                            const bool laneRun = hasRun && k < colRuns && gl + 1 < totalRuns; // a boundary lane followed by the run's other boundary
+                            const uint32_t el = laneRun ? (ITER > 0 ? rec.y : nextEl) : 0x0000ffffu; // others: air of length 0, never solid
+                            r_ci = (int)(short)(el & 0xffffu); r_len = (int)(short)(el >> 16);           // RLEElement World.cs:245-259
+                            if (ITER > 0) { r_eMax = (float)yB; r_eMin = (float)nextY; } else { r_eMin = (float)yB; r_eMax = (float)nextY; }
+
+                            STAMP(5);
+                            const F3 lMinLast = F3{planeBottom.x + planeDir.x * cDl, planeBottom.y + planeDir.y * cDl, planeBottom.z + planeDir.z * cDl}; // :289-293
+                            const F3 lMinNext = F3{planeBottom.x + planeDir.x * cDn, planeBottom.y + planeDir.y * cDn, planeBottom.z + planeDir.z * cDn};
+                            const F3 lMaxLast = F3{planeTop.x + planeDir.x * cDl, planeTop.y + planeDir.y * cDl, planeTop.z + planeDir.z * cDl};
+                            const F3 lMaxNext = F3{planeTop.x + planeDir.x * cDn, planeTop.y + planeDir.y * cDn, planeTop.z + planeDir.z * cDn};
+                            const float portion = world.y_pow2 ? (float)yB * world.inv_dim_y : unlerpf(0.0f, worldMaxY, (float)yB); // :478-479
+                            const F3 Fp = lerp3(lMinLast, lMaxLast, portion), Np = lerp3(lMinNext, lMaxNext, portion);
+                            bFx = Fp.x; bFy = Fp.y; bFz = Fp.z;
+                            const bool fFront = !(Fp.y <= 0.0f), nFront = !(Np.y <= 0.0f); // in front of the near plane (CameraData.cs:126,143)
+                            // which run's cap ends on this boundary: the run below it when it is seen from above (:549), the run above it
+                            // when seen from below (:556); a run takes the first of the two that applies
+                            const int bKind = portion < cameraPosYNormalized ? 1 : (portion > cameraPosYNormalized ? 2 : 0);
+                            const float fpx = Fp.x / Fp.z;
+                            const int fr = f2i(rintf(fpx));
+                            int bcMin = 0, bcMax = 0;
+                            if (bKind && fFront && nFront) { // :571-578
+                                const int nr = f2i(rintf(Np.x / Np.z));
+                                bcMin = nr; bcMax = fr;
+                                if (bcMin > bcMax) { bcMin = fr; bcMax = nr; }
+                            }
+                            const int flags = (fFront ? 1 : 0) | (nFront ? 2 : 0) | (bKind << 2);
+                            const float nextFpx = __shfl_down_sync(gmask, fpx, 1, G);
+                            const int nextFlags = __shfl_down_sync(gmask, flags, 1, G);
+                            const int nextCMin = __shfl_down_sync(gmask, bcMin, 1, G), nextCMax = __shfl_down_sync(gmask, bcMax, 1, G);
+                            const bool nextFront = nextFlags & 1;
+                            const int topKind = ITER > 0 ? bKind : (nextFlags >> 2), botKind = ITER > 0 ? (nextFlags >> 2) : bKind;
+                            r_capKind = topKind == 1 ? 1 : (botKind == 2 ? 2 : 0); // :549,556
+                            const bool capOwn = (r_capKind == 1) == (ITER > 0);      // the cap's boundary is this lane's (else the next lane's)
+                            const bool capNFront = capOwn ? nFront : ((nextFlags & 2) != 0);
+                            r_sideClip = false; r_capClip = false;
+                            const bool solidRun = laneRun && r_ci >= 0;
+                            r_solid = solidRun;
+                            bool needExact = false;
+                            if (solidRun) {
+                                if (fFront && nextFront) {
+                                    // both ends in front of the near plane: ClipHomogeneousCameraSpaceLine changes nothing
+                                    const float fb = ITER > 0 ? nextFpx : fpx, ft = ITER > 0 ? fpx : nextFpx; // bottom / top end
+                                    const int nextFr = f2i(rintf(nextFpx));
+                                    const int rb = ITER > 0 ? nextFr : fr, rt = ITER > 0 ? fr : nextFr;
+                                    if (fb > ft) { r_sMin = rt; r_sMax = rb; } else { r_sMin = rb; r_sMax = rt; } // :496-502
+                                    r_sideClip = true;
+                                    if (r_capKind) {
+                                        if (capNFront) { r_cMin = capOwn ? bcMin : nextCMin; r_cMax = capOwn ? bcMax : nextCMax; r_capClip = true; }
+                                        else needExact = true;
+                                    }
+                                } else if (!fFront && !nextFront) {
+                                    // both ends behind: no side span; the cap's last-line end is behind too, so the cap exists only if its
+                                    // next-line end is in front (and then it is clipped)
+                                    if (r_capKind && capNFront) needExact = true;
+                                } else needExact = true;
+                                if (r_capKind) r_capColor = __ldg(colElems + colRuns + 2 + (r_capKind == 1 ? r_ci : r_ci + r_len - 1)); // :553,560
+                            }
+                            if (GBALLOT(needExact)) {
+                                EMU_STAT(8); // rounds with a run straddling the near plane
+                                // ---- a run straddles the near plane: the reference's per-run clipping (rare; columns next to the camera)
+                                const F3 nF = F3{__shfl_down_sync(gmask, Fp.x, 1, G), __shfl_down_sync(gmask, Fp.y, 1, G), __shfl_down_sync(gmask, Fp.z, 1, G)};
+                                const F3 nN = F3{__shfl_down_sync(gmask, Np.x, 1, G), __shfl_down_sync(gmask, Np.y, 1, G), __shfl_down_sync(gmask, Np.z, 1, G)};
+                                if (needExact) {
+                                    F3 frontBottom = ITER > 0 ? nF : Fp, frontTop = ITER > 0 ? Fp : nF;
+                                    float uA = (float)r_len, uB = 0.0f;
+                                    r_sideClip = false; r_capClip = false;
+                                    if (clip_near_u(frontBottom, frontTop, uA, uB)) { // :489-502 (clips frontBottom/Top in place)
+                                        float bfx = frontBottom.x / frontBottom.z, bfy = frontTop.x / frontTop.z;
+                                        if (bfx > bfy) { float t = bfx; bfx = bfy; bfy = t; }
+                                        r_sMin = f2i(rintf(bfx)); r_sMax = f2i(rintf(bfy));
+                                        r_sideClip = true;
+                                    }
+                                    if (r_capKind) { // :554-578
+                                        F3 secA = capOwn ? Np : nN, secB = r_capKind == 1 ? frontTop : frontBottom;
+                                        if (clip_near(secA, secB)) {
+                                            r_cMin = f2i(rintf(secA.x / secA.z)); r_cMax = f2i(rintf(secB.x / secB.z));
+                                            if (r_cMin > r_cMax) { int t = r_cMin; r_cMin = r_cMax; r_cMax = t; }
+                                            r_capClip = true;
+                                        }
+                                    }
+                                }
+                            }
+                        } else {
+                            uint32_t el = 0u;
+                            if (hasRun) el = __ldg(colElems + (ITER > 0 ? 1 + k : colRuns - k));
+                            r_ci = (int)(short)(el & 0xffffu); r_len = (int)(short)(el >> 16); // RLEElement World.cs:245-259
+                            roundInvalid = GBALLOT(hasRun && r_len == 0);  // an invalid element (Length == 0) ends its column (:445-447)
+                            // lanes of my column from its start up to me, and whether an invalid element precedes me there
+                            const uint32_t mineUpToMe = ((2u << gl) - 1u) & ~((1u << myStart) - 1u);
+                            const bool valid = hasRun && !(roundInvalid & mineUpToMe);
+                            r_solid = valid && r_ci >= 0;
+                            const int span = valid ? r_len * cScale : 0;
+                            int sum = span;
+    #pragma unroll
+                            for (int o = 1; o < G; o <<= 1) { int t = __shfl_up_sync(gmask, sum, o, G); if (gl >= o) sum += t; }
+                            const int before = GSHFL(sum, myStart > 0 ? myStart - 1 : 0);
+                            const int inclCol = sum - (myStart > 0 ? before : 0) + (myCol == c ? yDone : 0); // my column's runs up to and including me
+                            if (tall) yDone = GSHFL(inclCol, runsHere - 1);                // extent after this pass (the round holds only this column)
+                            if (ITER > 0) { r_eMax = (float)(world.dim_y - (inclCol - span)); r_eMin = (float)(world.dim_y - inclCol); } // :449-455
+                            else          { r_eMin = (float)(inclCol - span); r_eMax = (float)inclCol; }
+
+                            STAMP(5);
+                            const F3 lMinLast = F3{planeBottom.x + planeDir.x * cDl, planeBottom.y + planeDir.y * cDl, planeBottom.z + planeDir.z * cDl}; // :289-293
+                            const F3 lMinNext = F3{planeBottom.x + planeDir.x * cDn, planeBottom.y + planeDir.y * cDn, planeBottom.z + planeDir.z * cDn};
+                            const F3 lMaxLast = F3{planeTop.x + planeDir.x * cDl, planeTop.y + planeDir.y * cDl, planeTop.z + planeDir.z * cDl};
+                            const F3 lMaxNext = F3{planeTop.x + planeDir.x * cDn, planeTop.y + planeDir.y * cDn, planeTop.z + planeDir.z * cDn};
+                            r_sideClip = false; r_capClip = false; r_capKind = 0;
+                            {
+                                float bfx = 0.0f, bfy = 0.0f, uvAx = 0.0f, uvAy = 0.0f, uvBx = 0.0f, uvBy = 0.0f;
+                                int capIdx = 0;
+                                const float portionBottom = unlerpf(0.0f, worldMaxY, r_eMin); // :478-481
+                                const float portionTop = unlerpf(0.0f, worldMaxY, r_eMax);
+                                F3 frontBottom = lerp3(lMinLast, lMaxLast, portionBottom);
+                                F3 frontTop = lerp3(lMinLast, lMaxLast, portionTop);
+                                // which cap, if any, depends on the camera height only (:549,556); its flat colour (:553,560) is fetched
+                                // now, while the divisions below run, and parked in the cache
+                                if (portionTop < cameraPosYNormalized) { r_capKind = 1; capIdx = r_ci; }
+                                else if (portionBottom > cameraPosYNormalized) { r_capKind = 2; capIdx = r_ci + r_len - 1; }
+                                uint32_t capColor = 0u;
+                                if (r_capKind && valid && r_ci >= 0) capColor = __ldg(colElems + colRuns + 2 + capIdx);
+                                float uA = (float)r_len, uB = 0.0f;
+                                if (clip_near_u(frontBottom, frontTop, uA, uB)) { // :489-502 (clips frontBottom/Top in place)
+                                    uvAx = 1.0f / frontBottom.z; uvAy = uA / frontBottom.z;
+                                    uvBx = 1.0f / frontTop.z;    uvBy = uB / frontTop.z;
+                                    bfx = frontBottom.x / frontBottom.z; bfy = frontTop.x / frontTop.z;
+                                    if (bfx > bfy) {
+                                        float t = bfx; bfx = bfy; bfy = t;
+                                        t = uvAx; uvAx = uvBx; uvBx = t;
+                                        t = uvAy; uvAy = uvBy; uvBy = t;
+                                    }
+                                    r_sMin = f2i(rintf(bfx)); r_sMax = f2i(rintf(bfy));
+                                    r_sideClip = true;
+                                }
+                                if (r_capKind) { // :554-578
+                                    const float portion = r_capKind == 1 ? portionTop : portionBottom;
+                                    F3 secA = lerp3(lMinNext, lMaxNext, portion), secB = r_capKind == 1 ? frontTop : frontBottom;
+                                    if (clip_near(secA, secB)) {
+                                        r_cMin = f2i(rintf(secA.x / secA.z)); r_cMax = f2i(rintf(secB.x / secB.z));
+                                        if (r_cMin > r_cMax) { int t = r_cMin; r_cMin = r_cMax; r_cMax = t; }
+                                        r_capClip = true;
+                                    }
+                                }
+                                cache[0 * G + gl] = __float_as_uint(bfx);  cache[1 * G + gl] = __float_as_uint(bfy);
+                                cache[2 * G + gl] = __float_as_uint(uvAx); cache[3 * G + gl] = __float_as_uint(uvAy);
+                                cache[4 * G + gl] = __float_as_uint(uvBx); cache[5 * G + gl] = __float_as_uint(uvBy);
+                                cache[6 * G + gl] = (uint32_t)r_len;       cache[7 * G + gl] = capColor;
+                                __syncwarp(gmask);
+                            }
+                        }
+                        STAMP(6);
+                        roundHotS = GBALLOT(r_solid && r_sideClip && span_would_write(rw, r_sMin, r_sMax));
+                        roundHotC = GBALLOT(r_solid && r_capClip && span_would_write(rw, r_cMin, r_cMax));
+                        STAMP(4);
+                    }
+
+                    // ---- resolve this column (pass) against the current frustum / written-pixel state (:441-611) -----------
+                    const int base = GSHFL(myBase, c);
+                    const uint32_t colMask = (runsHere >= 32 ? FULL_MASK : ((1u << runsHere) - 1u)) << base;
+                    const bool inCol = (colMask >> gl) & 1u;
+                    const uint32_t invalidHere = roundInvalid & colMask;
+                    const int endValid = invalidHere ? __ffs(invalidHere) - 1 : base + runsHere; // first lane past the valid runs
+                    const bool solid = inCol && gl < endValid && r_ci >= 0; // valid and !IsAir
+                    const bool above = r_eMin > worldBoundsMax, below = r_eMax < worldBoundsMin;
+                    const bool isBreak = solid && (ITER > 0 ? (!above && below) : above); // :461-475 (above is tested first)
+                    const uint32_t breakMask = GBALLOT(isBreak);
+                    const int endVisit = breakMask ? __ffs(breakMask) : endValid;           // the breaking run itself was dereferenced
+                    if (invalidHere | breakMask) colStop = true;
+                    const bool active = solid && gl < endVisit && !above && !below;
+                    const bool sideOk = active && r_sideClip;
+                    const bool capOk = active && r_capClip &&
+                                       (r_capKind == 1 ? !(r_eMax > worldBoundsMax) : !(r_eMin < worldBoundsMin)); // :549-565
+
+                    STAMP(6);
+                    // ---- commit, in reference order (side of run j, cap of run j, side of run j+1, ...), only the spans that still
+                    // hold an unwritten pixel; everything ordered before the committed span is a no-op now and stays one (written
+                    // pixels only grow, the writable range only shrinks), so it is retired with it.
+                    uint32_t candS = GBALLOT(sideOk) & roundHotS, candC = GBALLOT(capOk) & roundHotC;
+                    int visitedHere = endVisit - base;
+                    while (candS | candC) {
+                        const int jS = candS ? __ffs(candS) - 1 : 64, jC = candC ? __ffs(candC) - 1 : 64;
+                        const bool isCap = jC < jS;
+                        const int j = isCap ? jC : jS;
+                        if (isCap) candC &= candC - 1u; else candS &= candS - 1u;
+                        int bMin = GSHFL(isCap ? r_cMin : r_sMin, j), bMax = GSHFL(isCap ? r_cMax : r_sMax, j);
+                        EMU_STAT(5); // commit candidates examined
+                        STAMP(8);
+                        if (!span_would_write(rw, bMin, bMax)) { STAMP(6); continue; } // written over / cut off since the round was formed
+                        EMU_STAT(6); // spans committed (each writes at least one pixel)
+                        if (isCap) EMU_STAT(7);
+                        STAMP(9);
+                        reduce_pixel_horizon(rw, bMin, bMax); // :507-517 / :583-593
+                        STAMP(10);
+                        if (isCap) {
+                            const uint32_t color = FAST ? GSHFL(r_capColor, j) : cache[7 * G + j];
+                            for (int y = bMin + gl; y <= bMax; y += G) // :595-602
+                                if (!((rw.seen[y >> 5] >> (y & 31)) & 1u)) row[y] = color;
+                        } else {
+                            STAMP(11);
+                            float jbfx, jbfy, jAx, jAy, jBx, jBy;
+                            int jLen;
+                            const int jCi = GSHFL(r_ci, j);
+                            if (FAST) {
+                                // the perspective-correct u of :490-491,525-530 is needed only now, for the one span that writes, and
+                                // only if the run is longer than one voxel (clamp(floor(u), 0, Length - 1) is 0 otherwise): rebuild the
+                                // span's ends from the boundary points of lanes j and j + 1 exactly as :478-502 does
+                                jLen = GSHFL(r_len, j);
+                                jbfx = jbfy = jAx = jAy = jBx = jBy = 0.0f;
+                                if (jLen > 1) {
+                                    const F3 pj = F3{GSHFL(bFx, j), GSHFL(bFy, j), GSHFL(bFz, j)}, pn = F3{GSHFL(bFx, j + 1), GSHFL(bFy, j + 1), GSHFL(bFz, j + 1)};
+                                    F3 frontBottom = ITER > 0 ? pn : pj, frontTop = ITER > 0 ? pj : pn;
+                                    float uA = (float)jLen, uB = 0.0f;
+                                    clip_near_u(frontBottom, frontTop, uA, uB);
+                                    jAx = 1.0f / frontBottom.z; jAy = uA / frontBottom.z;
+                                    jBx = 1.0f / frontTop.z;    jBy = uB / frontTop.z;
+                                    jbfx = frontBottom.x / frontBottom.z; jbfy = frontTop.x / frontTop.z;
+                                    if (jbfx > jbfy) {
+                                        float t = jbfx; jbfx = jbfy; jbfy = t;
+                                        t = jAx; jAx = jBx; jBx = t;
+                                        t = jAy; jAy = jBy; jBy = t;
+                                    }
+                                }
+                            } else {
+                                jbfx = __uint_as_float(cache[0 * G + j]); jbfy = __uint_as_float(cache[1 * G + j]);
+                                jAx = __uint_as_float(cache[2 * G + j]); jAy = __uint_as_float(cache[3 * G + j]);
+                                jBx = __uint_as_float(cache[4 * G + j]); jBy = __uint_as_float(cache[5 * G + j]);
+                                jLen = (int)cache[6 * G + j];
+                            }
+                            STAMP(12);
+                            for (int y = bMin + gl; y <= bMax; y += G) { // :519-533
+                                if (!((rw.seen[y >> 5] >> (y & 31)) & 1u)) {
+                                    int idx = jCi;
+                                    if (!FAST || jLen > 1) {
+                                        float l = unlerpf(jbfx, jbfy, (float)y);
+                                        float wx = lerpf(jAx, jBx, l), wy = lerpf(jAy, jBy, l);
+                                        float u = wy / wx;
+                                        idx = max(0, min(jLen - 1, f2i(floorf(u)))) + jCi;
+                                    }
+                                    row[y] = __ldg(colColors + idx);
+                                }
+                            }
+                        }
+                        STAMP(13);
+                        __syncwarp(gmask);
+                        { const int fresh = mark_seen<G>(rw.seen, bMin, bMax, gl); if (COUNTERS) acc.px_voxel += fresh; }
+                        __syncwarp(gmask);
+                        STAMP(6);
+                        frustumDirMaxWorld = EPS; // a pixel was written (:522,598)
+                        if (rw.nf_min > rw.nf_max) { terminated = true; visitedHere = j + 1 - base; break; } // :535-539,604-608
+                    }
+                    if (COUNTERS && gl == 0) acc.runs_visited += visitedHere;
+                    if (tall) { k0 += FAST ? G - 1 : G; roundCols = 0u; } // the cache held one pass of this column only
+                } while (tall && k0 < runCount && !colStop && !terminated);
+                STAMP(4);
+                if (terminated) { cellsDone = c + 1; break; }
+            }
+            if (COUNTERS && gl == 0) acc.dda_steps += cellsDone;
+            if (endKind != 0) reachedEnd = true;
+        }
+        STAMP(7);
+        // WriteSkybox :699-708 — :248,268,323,401,419,537,606,619 all end here
+        __syncwarp(gmask);
+        for (int y = rw.orig_min + gl; y <= rw.orig_max; y += G)
+            if (!((rw.seen[y >> 5] >> (y & 31)) & 1u)) row[y] = SKYBOX_ARGB;
+        if (COUNTERS) {
+            for (int w = (rw.orig_min >> 5) + gl; w <= (rw.orig_max >> 5); w += G) {
+                uint32_t m = FULL_MASK;
+                if (w == (rw.orig_min >> 5)) m &= mask_from(rw.orig_min);
+                if (w == (rw.orig_max >> 5)) m &= mask_to(rw.orig_max);
+                acc.px_sky += __popc(~rw.seen[w] & m);
+            }
+        }
     }
 
     STAMP(0);
