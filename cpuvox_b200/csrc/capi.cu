@@ -152,6 +152,7 @@ void make_blit(cvx_ctx* ctx, const cvxd_frame& f, uint32_t* target, cvxd_blit& b
     b.ray_begin = 0; b.ray_end = f.total_rays; b.owned_only = 0;
     b.td = ctx->td; b.lr = ctx->lr;
     b.frame = target;
+    cvxd_blit_prepare(&b);
 }
 
 int check_ready(cvx_ctx* ctx, const void* setup) {

@@ -95,7 +95,25 @@ struct cvxd_blit {
     const uint32_t* td;
     const uint32_t* lr;
     uint32_t* frame;
+    /* per-segment constants of the row formula (RenderManager.cs:235-242), filled by cvxd_blit_prepare on the host: _RayScale, _RayOffset
+     * (two IEEE divisions a tile would otherwise repeat), the first raybuffer row of the segment and the flat index of its first ray */
+    float seg_scale[4], seg_offset[4];
+    int32_t seg_off01[4], seg_flat_base[4];
 };
+
+static inline void cvxd_blit_prepare(cvxd_blit* b) {
+    int flat = 0;
+    for (int k = 0; k < 4; k++) {
+        const int rows = k < 2 ? b->width + 2 * b->height : 2 * b->width + b->height;
+        const float rowsF = (float)rows;
+        const int off01 = k == 1 ? b->seg[0].ray_count : (k == 3 ? b->seg[2].ray_count : 0);
+        b->seg_scale[k] = (float)b->seg[k].ray_count / rowsF;
+        b->seg_off01[k] = off01;
+        b->seg_offset[k] = (k == 1 || k == 3) ? (float)off01 / rowsF : 0.0f;
+        b->seg_flat_base[k] = flat;
+        flat += b->seg[k].ray_count > 0 ? b->seg[k].ray_count : 0;
+    }
+}
 
 static inline void cvxd_frame_set_world(cvxd_frame* f, const cvxd_world* w) { f->cam_y_norm = f->pos_y / w->dim_y_f; }
 

@@ -977,11 +977,10 @@ __device__ __forceinline__ P2Seg p2_seg(const cvxd_blit& p, int k) {
     const int rows = k < 2 ? p.width + 2 * p.height : 2 * p.width + p.height;
     g.rc = p.seg[k].ray_count;
     g.rowsF = (float)rows;
-    g.scale = (float)g.rc / g.rowsF;
-    g.off01 = k == 1 ? p.seg[0].ray_count : (k == 3 ? p.seg[2].ray_count : 0);
-    g.offset = (k == 1 || k == 3) ? (float)g.off01 / g.rowsF : 0.0f;
-    g.flatBase = 0;
-    for (int j = 0; j < k; j++) g.flatBase += max(0, p.seg[j].ray_count);
+    g.scale = p.seg_scale[k];        // (float)rc / rowsF and (float)off01 / rowsF, divided once on the host (cvxd_blit_prepare)
+    g.off01 = p.seg_off01[k];
+    g.offset = p.seg_offset[k];
+    g.flatBase = p.seg_flat_base[k];
     return g;
 }
 
@@ -1071,13 +1070,14 @@ phase2_kernel(const __grid_constant__ cvxd_blit p) {
     // ---- the segment that holds the whole tile, if one does: lanes 0..3 of warp 0 test one corner pixel each against every
     // segment; the verdict and that segment's constants go to the other warps through shared memory
     if (warp == 0) {
+        // 16 lanes: lane = 4 * segment + corner tests one corner pixel against one segment; a segment holds the tile if its four lanes agree
         int u = -1;
-        const float px = (float)((lane & 1) ? xLast : x0) + 0.5f, py = (float)((lane & 2) ? yLast : y0) + 0.5f;
-        const float dx = px - p.vp_x, dy = py - p.vp_y;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
+        {
+            const int k = (lane >> 2) & 3;
+            const float px = (float)((lane & 1) ? xLast : x0) + 0.5f, py = (float)((lane & 2) ? yLast : y0) + 0.5f;
+            const float dx = px - p.vp_x, dy = py - p.vp_y;
             bool in = false;
-            if (p.seg[k].ray_count > 0) {
+            if (lane < 16 && p.seg[k].ray_count > 0) {
                 const float e1x = p.seg[k].max_screen[0] - p.vp_x, e1y = p.seg[k].max_screen[1] - p.vp_y;
                 const float e2x = p.seg[k].min_screen[0] - p.vp_x, e2y = p.seg[k].min_screen[1] - p.vp_y;
                 const float det = e1x * e2y - e1y * e2x;
@@ -1088,8 +1088,9 @@ phase2_kernel(const __grid_constant__ cvxd_blit p) {
                 const float nb = (tb0 - tb1) * sgn, nc = (tc0 - tc1) * sgn;
                 in = fabsf(det) > 1e-20f && fabsf(det) < 1e30f && nb > 1e-5f * (fabsf(tb0) + fabsf(tb1)) && nc > 1e-5f * (fabsf(tc0) + fabsf(tc1));
             }
-            const uint32_t m = __ballot_sync(FULL_MASK, in) & 0xfu;
-            if (u < 0 && m == 0xfu) u = k;
+            const uint32_t m = __ballot_sync(FULL_MASK, in);
+#pragma unroll
+            for (int j = 3; j >= 0; j--) if (((m >> (4 * j)) & 0xfu) == 0xfu) u = j;   // the first segment that holds all four corners
         }
         P2Seg g;
         if (u >= 0) g = p2_seg(p, u);
